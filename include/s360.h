@@ -1,0 +1,180 @@
+/* s360.h — C ABI of the B200-native Surround360 stereo-panorama render path.
+ *
+ * Drop-in boundary for surround360_render's per-frame renderer
+ * (surround360_render/source/test/TestRenderStereoPanorama.cpp). The reference has no
+ * FFI layer; these entry points are what a C++ shim placed under the reference's
+ * in-process operator API would bind (see INTEGRATION.md for the ~30-line adapters):
+ *
+ *   s360_flow_*            <- OpticalFlowInterface::computeOpticalFlow
+ *                             (source/optical_flow/OpticalFlowInterface.h:34-41) as created by
+ *                             makeOpticalFlowByName (source/optical_flow/OpticalFlowFactory.h:23-64)
+ *   s360_novel_view_chunk  <- NovelViewGenerator::prepare + combineLazyNovelViews
+ *                             (source/optical_flow/NovelView.h:79-138, NovelView.cpp:226-299)
+ *   s360_project_spherical <- bicubicRemapToSpherical (source/render/ImageWarper.h:59-66) with
+ *                             projectSideToSpherical's alpha ramp (TRSP:99-135)
+ *   s360_flatten_deghost   <- flattenLayersDeghostPreferBase (source/util/CvUtil.h:72-74)
+ *   s360_feather_alpha     <- featherAlphaChannel (source/util/CvUtil.cpp:140-157)
+ *   s360_sharpen           <- iirLowPass + sharpenWithIirLowPass (source/util/Filter.h:39-137)
+ *   s360_cubemap           <- convertSphericalToCubemapBicubicRemap + stackOutputCubemapFaces
+ *                             (source/render/ImageWarper.h:53-57, source/util/CvUtil.cpp:117-138)
+ *   s360_resize_cubic      <- cv::resize(INTER_CUBIC) at TRSP:943-956
+ *   s360_render_frame      <- renderStereoPanorama() (TRSP:716-972) minus file I/O
+ *   s360_rig_*             <- Camera::loadRig / RigDescription (source/render/Camera.cpp:243-254,
+ *                             source/render/RigDescription.cpp:18-78)
+ *
+ * Conventions: plain pointers and sizes; images are tightly packed row-major unless a
+ * stride is given; BGRA8 / BGR8 / float2 flow exactly as the reference's cv::Mat types
+ * (CV_8UC4 / CV_8UC3 / CV_32FC2). Every function returns 0 on success, non-zero on error
+ * (no exceptions cross the ABI); s360_last_error() returns the message for the calling
+ * thread. A context is bound to one CUDA device and must not be shared between host
+ * threads concurrently. Buffers are owned by the caller. `_dev` variants take device
+ * pointers (same layout) and enqueue on the context's stream without synchronising.
+ * There is no CPU fallback: if the CUDA device or kernels are unavailable the call fails.
+ */
+#ifndef S360_H
+#define S360_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s360_ctx s360_ctx;
+
+/* OpticalFlowInterface::DirectionHint (OpticalFlowInterface.h:24) — same numeric order */
+typedef enum { S360_HINT_UNKNOWN = 0, S360_HINT_RIGHT = 1, S360_HINT_DOWN = 2, S360_HINT_LEFT = 3, S360_HINT_UP = 4 } s360_hint;
+
+/* Pixel-affecting gflags of TRSP:44-70 (same names, same defaults via s360_params_default) */
+typedef struct {
+  double interpupilary_dist;      /* 6.4 */
+  double sharpening;              /* 0.0 */
+  double zero_parallax_dist;      /* 10000.0 */
+  int side_alpha_feather_size;    /* 100 */
+  int std_alpha_feather_size;     /* 31 */
+  int enable_top;                 /* 0 */
+  int enable_bottom;              /* 0 */
+  int eqr_width;                  /* 256 */
+  int eqr_height;                 /* 128 */
+  int final_eqr_width;            /* 3480 */
+  int final_eqr_height;           /* 960 */
+  int cubemap_width;              /* 1536 */
+  int cubemap_height;             /* 1536 */
+  int want_cubemap;               /* output_cubemap_path non-empty */
+  int cubemap_photo;              /* cubemap_format == "photo" (default "video") */
+  char side_flow_alg[32];         /* "pixflow_low" */
+  char polar_flow_alg[32];        /* "pixflow_low" */
+} s360_params;
+
+const char* s360_last_error(void);
+const char* s360_version(void);
+void s360_params_default(s360_params* p);
+
+/* ---- context ---- */
+int s360_ctx_create(int device, s360_ctx** out);
+void s360_ctx_destroy(s360_ctx* ctx);
+int s360_ctx_synchronize(s360_ctx* ctx);
+/* cudaStream_t of the context, as void* (for callers that enqueue their own work) */
+void* s360_ctx_stream(s360_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+unsigned long long s360_ctx_launch_count(s360_ctx* ctx);
+/* keep copies of the pre-sharpen eye images for s360_frame_intermediate("eyeL"/"eyeR") */
+int s360_ctx_set_keep_intermediates(s360_ctx* ctx, int on);
+
+/* ---- rig (RIG_JSON.md format) ---- */
+int s360_rig_load_file(s360_ctx* ctx, const char* json_path);
+int s360_rig_load_json(s360_ctx* ctx, const char* json_text);
+int s360_rig_num_cameras(s360_ctx* ctx);
+int s360_rig_num_side(s360_ctx* ctx);
+/* which: 0 = top, 1 = bottom, 2 = secondary bottom; returns index into the rig, <0 on error */
+int s360_rig_special_camera(s360_ctx* ctx, int which);
+/* index into the rig of side camera `side_idx` */
+int s360_rig_side_index(s360_ctx* ctx, int side_idx);
+const char* s360_rig_camera_id(s360_ctx* ctx, int cam);
+/* Camera::pixel (Camera.h:133-140), host evaluation in double */
+int s360_camera_pixel(s360_ctx* ctx, int cam, const double xyz[3], double out_xy[2]);
+/* Compact binary form of the parsed rig + projection tables, for the one-off NCCL broadcast:
+ * rank 0 serialises, every rank deserialises. */
+int s360_rig_serialize(s360_ctx* ctx, void* buf, size_t cap, size_t* used);
+int s360_rig_deserialize(s360_ctx* ctx, const void* buf, size_t len);
+
+/* ---- geometry derived from rig + params (TRSP:155-162,309-316,340-348) ---- */
+typedef struct {
+  int cam_w, cam_h, overlap_w, num_novel;
+  float h_radians, v_radians, fov_h_radians, slab_disp, shift_px;
+  int pole_h;   /* rows of the top/bottom spherical images (TRSP:607-610) */
+} s360_geometry;
+int s360_geometry_query(s360_ctx* ctx, const s360_params* p, s360_geometry* out);
+
+/* ---- operators (host-pointer variants; synchronous) ---- */
+
+/* bicubicRemapToSpherical (+ optional side alpha ramp). src: BGR8 (src_channels 3) or BGRA8
+ * (4). dst: BGRA8 dst_w x dst_h. feather > 0 applies projectSideToSpherical's ramp to the
+ * source rows (TRSP:116-125). */
+int s360_project_spherical(s360_ctx* ctx, int cam, const uint8_t* src, int src_w, int src_h, int src_channels,
+                           float left_angle, float right_angle, float top_angle, float bottom_angle, int feather,
+                           uint8_t* dst_bgra, int dst_w, int dst_h);
+
+/* computeOpticalFlow(I0BGRA, I1BGRA, prevFlow, prevI0BGRA, prevI1BGRA, flow, hint).
+ * prev_* may all be NULL (no temporal regularisation). flow: w*h float2. */
+int s360_flow_compute(s360_ctx* ctx, const char* alg_name, const uint8_t* i0_bgra, const uint8_t* i1_bgra, int w, int h,
+                      const float* prev_flow, const uint8_t* prev_i0_bgra, const uint8_t* prev_i1_bgra, float* flow_out,
+                      s360_hint hint);
+/* Batched variant: n independent pairs of identical size, solved concurrently. */
+int s360_flow_compute_batch(s360_ctx* ctx, const char* alg_name, int n, const uint8_t* const* i0_bgra,
+                            const uint8_t* const* i1_bgra, int w, int h, float* const* flow_out, const s360_hint* hints);
+
+/* NovelViewGeneratorLazyFlow::combineLazyNovelViews for one camera pair with the warp buffer
+ * of renderStereoPanoramaChunksThread (TRSP:259-292). Outputs two BGRA8 chunks buf_w x h. */
+int s360_novel_view_chunk(s360_ctx* ctx, const uint8_t* overlap_l, const uint8_t* overlap_r, const float* flow_l_to_r,
+                          const float* flow_r_to_l, int w, int h, int buf_w, int cam_w, int num_novel, float slab_disp,
+                          uint8_t* chunk_l, uint8_t* chunk_r);
+
+int s360_flatten_deghost(s360_ctx* ctx, const uint8_t* base_bgra, const uint8_t* top_bgra, int w, int h, uint8_t* out_bgra);
+int s360_feather_alpha(s360_ctx* ctx, const uint8_t* src_bgra, int w, int h, int erode_size, uint8_t* out_bgra);
+/* offsetHorizontalWrap (CvUtil.cpp:93-115), channels 3 or 4 */
+int s360_offset_wrap(s360_ctx* ctx, const uint8_t* src, int w, int h, int channels, float offset, uint8_t* out);
+/* sharpenThread (TRSP:688-696): in-place on BGR8 */
+int s360_sharpen(s360_ctx* ctx, uint8_t* bgr, int w, int h, double sharpening);
+/* both stages of TRSP:917-935 for one eye; out = stacked faces (video: 3*fw x 2*fh, photo: fw x 6*fh) */
+int s360_cubemap(s360_ctx* ctx, const uint8_t* eye_bgr, int w, int h, int face_w, int face_h, int photo, uint8_t* out_bgr);
+int s360_resize_cubic(s360_ctx* ctx, const uint8_t* src, int w, int h, int channels, int dst_w, int dst_h, uint8_t* dst);
+/* poleToSideFlowThread (TRSP:388-561): side BGRA8 sw x sh (padded eye panorama), fisheye
+ * BGRA8 fw x fh; warped_out BGRA8 sw x sh; flow_out (optional) int(fw*1.2) x fh float2 */
+int s360_pole_to_side(s360_ctx* ctx, const s360_params* p, const uint8_t* side_bgra, int sw, int sh,
+                      const uint8_t* fisheye_bgra, int fw, int fh, uint8_t* warped_out, float* flow_out);
+
+/* ---- whole frame ---- */
+
+/* renderStereoPanorama (TRSP:716-972) without file I/O. images: one BGR8 image per rig
+ * camera, in rig-JSON order, all img_w x img_h. equirect_out: BGR8, left eye over right eye;
+ * its size is given by s360_frame_output_size. cubemap_out may be NULL. Host pointers;
+ * copies in/out are part of the call. */
+int s360_frame_output_size(s360_ctx* ctx, const s360_params* p, int* eq_w, int* eq_h, int* cube_w, int* cube_h);
+int s360_render_frame(s360_ctx* ctx, const s360_params* p, const uint8_t* const* images_bgr, int img_w, int img_h,
+                      uint8_t* equirect_out, uint8_t* cubemap_out);
+/* Device-pointer variant: inputs/outputs already resident in HBM, enqueued on the context
+ * stream, no synchronisation (caller uses s360_ctx_synchronize or its own events). */
+int s360_render_frame_dev(s360_ctx* ctx, const s360_params* p, const uint8_t* const* images_bgr_dev, int img_w,
+                          int img_h, uint8_t* equirect_out_dev, uint8_t* cubemap_out_dev);
+
+/* Intermediates of the last s360_render_frame* call on this context, copied to host for
+ * stage-wise parity tests. name: "projection"(idx=side cam) "flowLtoR"/"flowRtoL"(idx=pair)
+ * "panoL" "panoR" "topSpherical" "bottomSpherical" "poleFlow"(0..3) "poleWarped"(0..3)
+ * "eyeL" "eyeR". Query size with out == NULL. is_float: 0 = uint8, 1 = float32. */
+int s360_frame_intermediate(s360_ctx* ctx, const char* name, int idx, void* out, int* w, int* h, int* channels,
+                            int* is_float);
+/* Per-stage device time (ms) of the last frame, measured with CUDA events on the context
+ * stream, in the order of the reference's runtime breakdown (TRSP:964-971):
+ * total, projection, side flow, novel view, pole flow+composite, sharpen, cubemap+resize */
+int s360_frame_stage_ms(s360_ctx* ctx, float out_ms[7]);
+
+/* ---- flow file format of saveFlowToFile/readFlowFromFile (CvUtil.cpp:159-199) ---- */
+int s360_flow_save(const char* path, const float* flow, int w, int h);
+int s360_flow_load(const char* path, float** flow_out, int* w, int* h); /* free with s360_free */
+void s360_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S360_H */

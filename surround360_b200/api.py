@@ -1,0 +1,299 @@
+"""Python host-side mirror of the reference's operator interface for the render path, over
+the C ABI in include/s360.h (libs360b200.so, hand-written sm_100a kernels).
+
+Names follow the reference: computeOpticalFlow / DirectionHint
+(source/optical_flow/OpticalFlowInterface.h:20-42), makeOpticalFlowByName's algorithm names
+(OpticalFlowFactory.h:23-64), bicubicRemapToSpherical (render/ImageWarper.h:59-66),
+flattenLayersDeghostPreferBase / featherAlphaChannel (util/CvUtil.h), sharpen
+(util/Filter.h), renderStereoPanorama (test/TestRenderStereoPanorama.cpp:716-972).
+
+There is no CPU fallback: importing works without a GPU (so the CPU test tier can check the
+exported symbols), but every call needs a B200 and fails loudly otherwise.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs360b200.so")
+
+
+class VrCamException(RuntimeError):
+    """Mirror of surround360::VrCamException (util/VrCamException.h:18)."""
+
+
+class S360Params(C.Structure):
+    _fields_ = [("interpupilary_dist", C.c_double), ("sharpening", C.c_double), ("zero_parallax_dist", C.c_double),
+                ("side_alpha_feather_size", C.c_int), ("std_alpha_feather_size", C.c_int),
+                ("enable_top", C.c_int), ("enable_bottom", C.c_int),
+                ("eqr_width", C.c_int), ("eqr_height", C.c_int), ("final_eqr_width", C.c_int),
+                ("final_eqr_height", C.c_int), ("cubemap_width", C.c_int), ("cubemap_height", C.c_int),
+                ("want_cubemap", C.c_int), ("cubemap_photo", C.c_int),
+                ("side_flow_alg", C.c_char * 32), ("polar_flow_alg", C.c_char * 32)]
+
+
+class S360Geometry(C.Structure):
+    _fields_ = [("cam_w", C.c_int), ("cam_h", C.c_int), ("overlap_w", C.c_int), ("num_novel", C.c_int),
+                ("h_radians", C.c_float), ("v_radians", C.c_float), ("fov_h_radians", C.c_float),
+                ("slab_disp", C.c_float), ("shift_px", C.c_float), ("pole_h", C.c_int)]
+
+
+class DirectionHint:  # OpticalFlowInterface.h:24
+    UNKNOWN, RIGHT, DOWN, LEFT, UP = range(5)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.s360_last_error.restype = C.c_char_p
+        L.s360_version.restype = C.c_char_p
+        L.s360_rig_camera_id.restype = C.c_char_p
+        L.s360_ctx_stream.restype = C.c_void_p
+        L.s360_ctx_launch_count.restype = C.c_ulonglong
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise VrCamException(lib().s360_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def default_params(**kw):
+    p = S360Params()
+    lib().s360_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v.encode() if isinstance(v, str) else v)
+    return p
+
+
+# quality presets of scripts/batch_process_video.py:176-199
+PRESETS = {
+    "3k": dict(eqr_width=3080, eqr_height=1540, final_eqr_width=3080, final_eqr_height=3080),
+    "4k": dict(eqr_width=4200, eqr_height=1024, final_eqr_width=4096, final_eqr_height=2048),
+    "6k": dict(eqr_width=6300, eqr_height=3072, final_eqr_width=6144, final_eqr_height=6144),
+    "8k": dict(eqr_width=8400, eqr_height=4096, final_eqr_width=8192, final_eqr_height=8192),
+}
+
+
+class Context:
+    """One render context = one CUDA device + stream (s360_ctx)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().s360_ctx_create(int(device), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().s360_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- rig ----
+    def load_rig(self, path):
+        _check(lib().s360_rig_load_file(self.h, path.encode()))
+
+    def load_rig_json(self, text):
+        _check(lib().s360_rig_load_json(self.h, text.encode()))
+
+    def rig_blob(self):
+        n = C.c_size_t()
+        _check(lib().s360_rig_serialize(self.h, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        _check(lib().s360_rig_serialize(self.h, _p(buf), buf.size, C.byref(n)))
+        return buf
+
+    def load_rig_blob(self, buf):
+        buf = _c(buf, np.uint8)
+        _check(lib().s360_rig_deserialize(self.h, _p(buf), buf.size))
+
+    n_cameras = property(lambda s: lib().s360_rig_num_cameras(s.h))
+    n_side = property(lambda s: lib().s360_rig_num_side(s.h))
+
+    def special_camera(self, which):
+        return lib().s360_rig_special_camera(self.h, which)
+
+    def side_index(self, i):
+        return lib().s360_rig_side_index(self.h, i)
+
+    def camera_id(self, cam):
+        return lib().s360_rig_camera_id(self.h, cam).decode()
+
+    def camera_pixel(self, cam, xyz):
+        o = np.zeros(2)
+        _check(lib().s360_camera_pixel(self.h, cam, _p(_c(xyz, np.float64)), _p(o)))
+        return o
+
+    def geometry(self, params):
+        g = S360Geometry()
+        _check(lib().s360_geometry_query(self.h, C.byref(params), C.byref(g)))
+        return g
+
+    # ---- operators ----
+    def bicubicRemapToSpherical(self, cam, src, dst_w, dst_h, left, right, top, bottom, feather=0):
+        src = _c(src, np.uint8)
+        out = np.zeros((dst_h, dst_w, 4), np.uint8)
+        _check(lib().s360_project_spherical(self.h, cam, _p(src), src.shape[1], src.shape[0], src.shape[2], C.c_float(left),
+                                            C.c_float(right), C.c_float(top), C.c_float(bottom), feather, _p(out), dst_w, dst_h))
+        return out
+
+    def computeOpticalFlow(self, alg_name, I0BGRA, I1BGRA, prevFlow=None, prevI0BGRA=None, prevI1BGRA=None,
+                           hint=DirectionHint.UNKNOWN):
+        i0, i1 = _c(I0BGRA, np.uint8), _c(I1BGRA, np.uint8)
+        h, w = i0.shape[:2]
+        flow = np.zeros((h, w, 2), np.float32)
+        pf = p0 = p1 = None
+        if prevFlow is not None:
+            pf, p0, p1 = _c(prevFlow, np.float32), _c(prevI0BGRA, np.uint8), _c(prevI1BGRA, np.uint8)
+        _check(lib().s360_flow_compute(self.h, alg_name.encode(), _p(i0), _p(i1), w, h, _p(pf) if pf is not None else None,
+                                       _p(p0) if p0 is not None else None, _p(p1) if p1 is not None else None, _p(flow), int(hint)))
+        return flow
+
+    def computeOpticalFlowBatch(self, alg_name, I0s, I1s, hints):
+        i0 = [_c(a, np.uint8) for a in I0s]
+        i1 = [_c(a, np.uint8) for a in I1s]
+        n = len(i0)
+        h, w = i0[0].shape[:2]
+        flows = [np.zeros((h, w, 2), np.float32) for _ in range(n)]
+        a0 = (C.c_void_p * n)(*[a.ctypes.data for a in i0])
+        a1 = (C.c_void_p * n)(*[a.ctypes.data for a in i1])
+        af = (C.c_void_p * n)(*[a.ctypes.data for a in flows])
+        hs = (C.c_int * n)(*[int(x) for x in hints])
+        _check(lib().s360_flow_compute_batch(self.h, alg_name.encode(), n, a0, a1, w, h, af, hs))
+        return flows
+
+    def combineLazyNovelViews(self, overlapL, overlapR, flowLtoR, flowRtoL, buf_w, cam_w, num_novel, slab_disp):
+        l, r = _c(overlapL, np.uint8), _c(overlapR, np.uint8)
+        flr, frl = _c(flowLtoR, np.float32), _c(flowRtoL, np.float32)
+        h, w = l.shape[:2]
+        oL = np.zeros((h, buf_w, 4), np.uint8)
+        oR = np.zeros_like(oL)
+        _check(lib().s360_novel_view_chunk(self.h, _p(l), _p(r), _p(flr), _p(frl), w, h, buf_w, cam_w, num_novel,
+                                           C.c_float(slab_disp), _p(oL), _p(oR)))
+        return oL, oR
+
+    def flattenLayersDeghostPreferBase(self, bottomLayer, topLayer):
+        b, t = _c(bottomLayer, np.uint8), _c(topLayer, np.uint8)
+        o = np.zeros_like(b)
+        _check(lib().s360_flatten_deghost(self.h, _p(b), _p(t), b.shape[1], b.shape[0], _p(o)))
+        return o
+
+    def featherAlphaChannel(self, src, erode_size):
+        s = _c(src, np.uint8)
+        o = np.zeros_like(s)
+        _check(lib().s360_feather_alpha(self.h, _p(s), s.shape[1], s.shape[0], erode_size, _p(o)))
+        return o
+
+    def offsetHorizontalWrap(self, src, offset):
+        s = _c(src, np.uint8)
+        o = np.zeros_like(s)
+        _check(lib().s360_offset_wrap(self.h, _p(s), s.shape[1], s.shape[0], s.shape[2], C.c_float(offset), _p(o)))
+        return o
+
+    def sharpen(self, bgr, sharpening):
+        o = _c(bgr, np.uint8).copy()
+        _check(lib().s360_sharpen(self.h, _p(o), o.shape[1], o.shape[0], C.c_double(sharpening)))
+        return o
+
+    def cubemap(self, eye_bgr, face_w, face_h, photo=False):
+        e = _c(eye_bgr, np.uint8)
+        o = np.zeros((6 * face_h, face_w, 3) if photo else (2 * face_h, 3 * face_w, 3), np.uint8)
+        _check(lib().s360_cubemap(self.h, _p(e), e.shape[1], e.shape[0], face_w, face_h, int(photo), _p(o)))
+        return o
+
+    def resizeCubic(self, src, dst_w, dst_h):
+        s = _c(src, np.uint8)
+        o = np.zeros((dst_h, dst_w, s.shape[2]), np.uint8)
+        _check(lib().s360_resize_cubic(self.h, _p(s), s.shape[1], s.shape[0], s.shape[2], dst_w, dst_h, _p(o)))
+        return o
+
+    def poleToSideFlow(self, params, side_bgra, fisheye_bgra):
+        s, f = _c(side_bgra, np.uint8), _c(fisheye_bgra, np.uint8)
+        ext_w = int(np.float32(f.shape[1]) * np.float32(1.2))
+        warped = np.zeros_like(s)
+        flow = np.zeros((f.shape[0], ext_w, 2), np.float32)
+        _check(lib().s360_pole_to_side(self.h, C.byref(params), _p(s), s.shape[1], s.shape[0], _p(f), f.shape[1], f.shape[0],
+                                       _p(warped), _p(flow)))
+        return warped, flow
+
+    # ---- whole frame ----
+    def output_size(self, params):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().s360_frame_output_size(self.h, C.byref(params), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def keep_intermediates(self, on=True):
+        _check(lib().s360_ctx_set_keep_intermediates(self.h, int(on)))
+
+    def renderStereoPanorama(self, params, images_bgr, equirect_out=None, cubemap_out=None):
+        """images_bgr: list (rig order) of HxWx3 uint8 host arrays (pinned or pageable)."""
+        ims = [_c(i, np.uint8) for i in images_bgr]
+        eq_w, eq_h, cw, ch = self.output_size(params)
+        eq = equirect_out if equirect_out is not None else np.zeros((eq_h, eq_w, 3), np.uint8)
+        cube = None
+        if cw > 0:
+            cube = cubemap_out if cubemap_out is not None else np.zeros((ch, cw, 3), np.uint8)
+        arr = (C.c_void_p * len(ims))(*[i.ctypes.data for i in ims])
+        _check(lib().s360_render_frame(self.h, C.byref(params), arr, ims[0].shape[1], ims[0].shape[0], _p(eq),
+                                       _p(cube) if cube is not None else None))
+        return (eq, cube) if cube is not None else eq
+
+    def render_frame_dev(self, params, image_ptrs, img_w, img_h, equirect_ptr, cubemap_ptr=None):
+        """Device-pointer variant; enqueues on the context stream without synchronising."""
+        arr = (C.c_void_p * len(image_ptrs))(*[int(p) for p in image_ptrs])
+        _check(lib().s360_render_frame_dev(self.h, C.byref(params), arr, img_w, img_h, C.c_void_p(int(equirect_ptr)),
+                                           C.c_void_p(int(cubemap_ptr)) if cubemap_ptr else None))
+
+    def synchronize(self):
+        _check(lib().s360_ctx_synchronize(self.h))
+
+    def stream(self):
+        return lib().s360_ctx_stream(self.h)
+
+    def launch_count(self):
+        return int(lib().s360_ctx_launch_count(self.h))
+
+    def stage_ms(self):
+        o = (C.c_float * 7)()
+        _check(lib().s360_frame_stage_ms(self.h, o))
+        names = ["total", "projection", "side_flow", "novel_view", "poles", "sharpen", "output"]
+        return dict(zip(names, list(o)))
+
+    def intermediate(self, name, idx=0):
+        w, h, c, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().s360_frame_intermediate(self.h, name.encode(), idx, None, C.byref(w), C.byref(h), C.byref(c), C.byref(f)))
+        out = np.zeros((h.value, w.value, c.value), np.float32 if f.value else np.uint8)
+        _check(lib().s360_frame_intermediate(self.h, name.encode(), idx, _p(out), C.byref(w), C.byref(h), C.byref(c), C.byref(f)))
+        return out
+
+
+def saveFlowToFile(flow, path):  # CvUtil.cpp:159-182
+    f = _c(flow, np.float32)
+    _check(lib().s360_flow_save(path.encode(), _p(f), f.shape[1], f.shape[0]))
+
+
+def readFlowFromFile(path):  # CvUtil.cpp:184-199
+    ptr = C.POINTER(C.c_float)()
+    w, h = C.c_int(), C.c_int()
+    _check(lib().s360_flow_load(path.encode(), C.byref(ptr), C.byref(w), C.byref(h)))
+    a = np.ctypeslib.as_array(ptr, shape=(h.value, w.value, 2)).copy()
+    lib().s360_free(ptr)
+    return a

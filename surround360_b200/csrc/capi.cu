@@ -1,0 +1,433 @@
+// C ABI (include/s360.h). Every entry point converts exceptions into a status code and a
+// thread-local message; nothing here falls back to the CPU.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include "pipeline.h"
+
+using namespace s360;
+
+namespace s360 { void initContextTables(s360_ctx* c); void resetPlan(s360_ctx* c); }
+
+static thread_local std::string g_lastError;
+#define S360_API_BEGIN try {
+#define S360_API_END                                             \
+  return 0;                                                      \
+  } catch (const std::exception& e) { g_lastError = e.what(); return 1; } \
+  catch (...) { g_lastError = "unknown error"; return 1; }
+
+static void require(bool ok, const char* msg) { if (!ok) throw std::runtime_error(msg); }
+static void useDevice(s360_ctx* c) { require(c != nullptr, "null context"); S360_CUDA_CHECK(cudaSetDevice(c->device)); }
+
+extern "C" {
+
+const char* s360_last_error(void) { return g_lastError.c_str(); }
+const char* s360_version(void) { return "surround360_b200 0.1 (sm_100a)"; }
+
+void s360_params_default(s360_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->interpupilary_dist = 6.4; p->sharpening = 0.0; p->zero_parallax_dist = 10000.0;
+  p->side_alpha_feather_size = 100; p->std_alpha_feather_size = 31;
+  p->eqr_width = 256; p->eqr_height = 128; p->final_eqr_width = 3480; p->final_eqr_height = 960;
+  p->cubemap_width = 1536; p->cubemap_height = 1536;
+  std::strcpy(p->side_flow_alg, "pixflow_low");
+  std::strcpy(p->polar_flow_alg, "pixflow_low");
+}
+
+int s360_ctx_create(int device, s360_ctx** out) {
+  S360_API_BEGIN
+  require(out != nullptr, "null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) throw std::runtime_error("no CUDA device available: this library has no CPU fallback");
+  require(device >= 0 && device < count, "device index out of range");
+  S360_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  S360_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) throw std::runtime_error(std::string("device '") + prop.name + "' is not sm_100a-class; kernels are built for B200 only");
+  auto c = std::make_unique<s360_ctx>();
+  c->device = device;
+  S360_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  initContextTables(c.get());
+  *out = c.release();
+  S360_API_END
+}
+void s360_ctx_destroy(s360_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  resetPlan(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+int s360_ctx_synchronize(s360_ctx* c) {
+  S360_API_BEGIN
+  useDevice(c);
+  S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  S360_API_END
+}
+void* s360_ctx_stream(s360_ctx* c) { return c ? (void*)c->stream : nullptr; }
+unsigned long long s360_ctx_launch_count(s360_ctx* c) { (void)c; return g_launchCount; }
+int s360_ctx_set_keep_intermediates(s360_ctx* c, int on) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  c->keepIntermediates = on != 0;
+  S360_API_END
+}
+
+// ---- rig ----
+int s360_rig_load_json(s360_ctx* c, const char* text) {
+  S360_API_BEGIN
+  require(c && text, "null argument");
+  Rig r;
+  r.parse(text);
+  c->rig = r;
+  c->rigLoaded = true;
+  resetPlan(c);
+  S360_API_END
+}
+int s360_rig_load_file(s360_ctx* c, const char* path) {
+  S360_API_BEGIN
+  require(c && path, "null argument");
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error(std::string("could not read JSON file: ") + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  Rig r;
+  r.parse(ss.str());
+  c->rig = r;
+  c->rigLoaded = true;
+  resetPlan(c);
+  S360_API_END
+}
+int s360_rig_num_cameras(s360_ctx* c) { return c && c->rigLoaded ? (int)c->rig.cameras.size() : -1; }
+int s360_rig_num_side(s360_ctx* c) { return c && c->rigLoaded ? (int)c->rig.side.size() : -1; }
+int s360_rig_special_camera(s360_ctx* c, int which) {
+  try {
+    require(c && c->rigLoaded, "no rig loaded");
+    return which == 0 ? c->rig.topCamera() : which == 1 ? c->rig.bottomCamera() : c->rig.findLargestDistCamAxisToRigCenter();
+  } catch (const std::exception& e) { g_lastError = e.what(); return -1; }
+}
+int s360_rig_side_index(s360_ctx* c, int i) {
+  if (!c || !c->rigLoaded || i < 0 || i >= (int)c->rig.side.size()) return -1;
+  return c->rig.side[i];
+}
+const char* s360_rig_camera_id(s360_ctx* c, int cam) {
+  if (!c || !c->rigLoaded || cam < 0 || cam >= (int)c->rig.cameras.size()) return nullptr;
+  return c->rig.cameras[cam].id.c_str();
+}
+int s360_camera_pixel(s360_ctx* c, int cam, const double xyz[3], double out[2]) {
+  S360_API_BEGIN
+  require(c && c->rigLoaded, "no rig loaded");
+  require(cam >= 0 && cam < (int)c->rig.cameras.size(), "camera index out of range");
+  c->rig.cameras[cam].pixel({xyz[0], xyz[1], xyz[2]}, out[0], out[1]);
+  S360_API_END
+}
+int s360_rig_serialize(s360_ctx* c, void* buf, size_t cap, size_t* used) {
+  S360_API_BEGIN
+  require(c && c->rigLoaded, "no rig loaded");
+  std::vector<uint8_t> b = c->rig.serialize();
+  if (used) *used = b.size();
+  if (buf) { require(cap >= b.size(), "buffer too small"); std::memcpy(buf, b.data(), b.size()); }
+  S360_API_END
+}
+int s360_rig_deserialize(s360_ctx* c, const void* buf, size_t len) {
+  S360_API_BEGIN
+  require(c && buf, "null argument");
+  Rig r;
+  r.deserialize((const uint8_t*)buf, len);
+  c->rig = r;
+  c->rigLoaded = true;
+  resetPlan(c);
+  S360_API_END
+}
+int s360_geometry_query(s360_ctx* c, const s360_params* p, s360_geometry* out) {
+  S360_API_BEGIN
+  require(c && c->rigLoaded && p && out, "no rig loaded / null argument");
+  const Geometry g = computeGeometry(c->rig, *p);
+  out->cam_w = g.camW; out->cam_h = g.camH; out->overlap_w = g.overlapW; out->num_novel = g.numNovel;
+  out->h_radians = g.hRadians; out->v_radians = g.vRadians; out->fov_h_radians = g.fovHRad; out->slab_disp = g.slabDisp;
+  out->shift_px = g.shiftPx; out->pole_h = g.poleH;
+  S360_API_END
+}
+
+// ---- operators ----
+int s360_project_spherical(s360_ctx* c, int cam, const uint8_t* src, int sw, int sh, int sc, float l, float r, float t, float b, int feather,
+                           uint8_t* dst, int dw, int dh) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(c->rigLoaded, "no rig loaded");
+  require(cam >= 0 && cam < (int)c->rig.cameras.size(), "camera index out of range");
+  require(src && dst && (sc == 3 || sc == 4) && sw > 0 && sh > 0 && dw > 0 && dh > 0, "bad image arguments");
+  cudaStream_t st = c->stream;
+  DeviceBuffer dRaw((size_t)sw * sh * sc), dSrc((size_t)sw * sh * 4), dDst((size_t)dw * dh * 4), dTab((size_t)(2 * dw + 2 * dh) * 4);
+  std::vector<float> tab((size_t)2 * dw + 2 * dh);
+  for (int x = 0; x < dw; ++x) {
+    const float xFrac = (x + 0.5f) / dw;
+    const float xAngle = (1 - xFrac) * l + xFrac * r;
+    tab[x] = cosf(xAngle); tab[dw + x] = sinf(xAngle);
+  }
+  for (int y = 0; y < dh; ++y) {
+    const float yFrac = (y + 0.5f) / dh;
+    const float yAngle = (1 - yFrac) * t + yFrac * b;
+    tab[2 * dw + y] = cosf(yAngle); tab[2 * dw + dh + y] = sinf(yAngle);
+  }
+  S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.p, src, dRaw.bytes, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dTab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+  launchPrepSource(st, dRaw.as<uint8_t>(), sc, sw, sh, feather, dSrc.as<uchar4>());
+  SphericalTables tb{dTab.as<float>(), dTab.as<float>() + dw, dTab.as<float>() + 2 * dw, dTab.as<float>() + 2 * dw + dh};
+  launchProjectSpherical(st, dSrc.as<uchar4>(), sw, sh, c->rig.cameras[cam].toDevice(), tb, dDst.as<uchar4>(), dw, dh, dw, 0, 0, 1, c->rt);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dst, dDst.p, (size_t)dw * dh * 4, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_flow_compute_batch(s360_ctx* c, const char* alg, int n, const uint8_t* const* i0, const uint8_t* const* i1, int w, int h,
+                            float* const* flowOut, const s360_hint* hints) {
+  S360_API_BEGIN
+  useDevice(c);
+  FlowParams fp;
+  if (!flowParamsByName(alg, &fp)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + (alg ? alg : "(null)"));
+  require(n >= 1 && n <= kMaxFlowBatch && w > 0 && h > 0 && i0 && i1 && flowOut, "bad flow arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer d0(px * 4 * n), d1(px * 4 * n), dF(px * 8 * n);
+  FlowImagePtrs ip{};
+  FlowPrevPtrs pv{};
+  for (int k = 0; k < n; ++k) {
+    S360_CUDA_CHECK(cudaMemcpyAsync(d0.as<uchar4>() + k * px, i0[k], px * 4, cudaMemcpyHostToDevice, st));
+    S360_CUDA_CHECK(cudaMemcpyAsync(d1.as<uchar4>() + k * px, i1[k], px * 4, cudaMemcpyHostToDevice, st));
+    ip.i0[k] = d0.as<uchar4>() + k * px; ip.i1[k] = d1.as<uchar4>() + k * px; ip.pitch0[k] = ip.pitch1[k] = w;
+    ip.hint[k] = hints ? (int)hints[k] : 0;
+  }
+  FlowBatch fb(n, w, h, fp);
+  fb.run(st, ip, pv, dF.as<float2>());
+  for (int k = 0; k < n; ++k) S360_CUDA_CHECK(cudaMemcpyAsync(flowOut[k], dF.as<float2>() + k * px, px * 8, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_flow_compute(s360_ctx* c, const char* alg, const uint8_t* i0, const uint8_t* i1, int w, int h, const float* prevFlow,
+                      const uint8_t* prevI0, const uint8_t* prevI1, float* flowOut, s360_hint hint) {
+  S360_API_BEGIN
+  useDevice(c);
+  FlowParams fp;
+  if (!flowParamsByName(alg, &fp)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + (alg ? alg : "(null)"));
+  require(w > 0 && h > 0 && i0 && i1 && flowOut, "bad flow arguments");
+  (void)prevI0;  // resized by the reference but never read (PixFlow.h:106, 109-117 use prevI1 only)
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer d0(px * 4), d1(px * 4), dF(px * 8), dPF, dP1;
+  S360_CUDA_CHECK(cudaMemcpyAsync(d0.p, i0, px * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(d1.p, i1, px * 4, cudaMemcpyHostToDevice, st));
+  FlowImagePtrs ip{};
+  FlowPrevPtrs pv{};
+  ip.i0[0] = d0.as<uchar4>(); ip.i1[0] = d1.as<uchar4>(); ip.pitch0[0] = ip.pitch1[0] = w; ip.hint[0] = (int)hint;
+  if (prevFlow) {
+    require(prevI1 != nullptr, "prev_flow given without prev images");
+    dPF.alloc(px * 8); dP1.alloc(px * 4);
+    S360_CUDA_CHECK(cudaMemcpyAsync(dPF.p, prevFlow, px * 8, cudaMemcpyHostToDevice, st));
+    S360_CUDA_CHECK(cudaMemcpyAsync(dP1.p, prevI1, px * 4, cudaMemcpyHostToDevice, st));
+    pv.enabled = true; pv.prevFlow[0] = dPF.as<float2>(); pv.prevI1[0] = dP1.as<uchar4>(); pv.prevPitch[0] = w;
+  }
+  FlowBatch fb(1, w, h, fp);
+  fb.run(st, ip, pv, dF.as<float2>());
+  S360_CUDA_CHECK(cudaMemcpyAsync(flowOut, dF.p, px * 8, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_novel_view_chunk(s360_ctx* c, const uint8_t* ovL, const uint8_t* ovR, const float* fLR, const float* fRL, int w, int h, int bufW,
+                          int camW, int numNovel, float slabDisp, uint8_t* chunkL, uint8_t* chunkR) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(ovL && ovR && fLR && fRL && chunkL && chunkR && w > 0 && h > 0 && bufW > 0, "bad novel view arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h, opx = (size_t)bufW * h;
+  DeviceBuffer dL(px * 4), dR(px * 4), dFLR(px * 8), dFRL(px * 8), dOL(opx * 4), dOR(opx * 4);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dL.p, ovL, px * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dR.p, ovR, px * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dFLR.p, fLR, px * 8, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dFRL.p, fRL, px * 8, cudaMemcpyHostToDevice, st));
+  launchNovelViewChunk(st, dL.as<uchar4>(), dR.as<uchar4>(), w, dFLR.as<float2>(), dFRL.as<float2>(), w, h, bufW, camW, numNovel, slabDisp,
+                       dOL.as<uchar4>(), dOR.as<uchar4>(), c->rt);
+  S360_CUDA_CHECK(cudaMemcpyAsync(chunkL, dOL.p, opx * 4, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(chunkR, dOR.p, opx * 4, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_flatten_deghost(s360_ctx* c, const uint8_t* base, const uint8_t* top, int w, int h, uint8_t* out) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(base && top && out && w > 0 && h > 0, "bad arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer dB(px * 4), dT(px * 4), dO(px * 4);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dB.p, base, px * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dT.p, top, px * 4, cudaMemcpyHostToDevice, st));
+  launchFlatten(st, dB.as<uchar4>(), dT.as<uchar4>(), w, h, dO.as<uchar4>());
+  S360_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, px * 4, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_feather_alpha(s360_ctx* c, const uint8_t* src, int w, int h, int erodeSize, uint8_t* out) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(src && out && w > 0 && h > 0, "bad arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer dS(px * 4), dO(px * 4), dScr(featherScratchBytes(w, h));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dS.p, src, px * 4, cudaMemcpyHostToDevice, st));
+  launchFeatherAlpha(st, dS.as<uchar4>(), w, h, erodeSize, c->blurKernelFor(erodeSize), dO.as<uchar4>(), dScr.as<uint8_t>());
+  S360_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, px * 4, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_offset_wrap(s360_ctx* c, const uint8_t* src, int w, int h, int channels, float offset, uint8_t* out) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(src && out && w > 0 && h > 0 && (channels == 3 || channels == 4), "bad arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer dRaw(px * channels), dS(px * 4), dO(px * 4), dOut(px * channels);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.p, src, px * channels, cudaMemcpyHostToDevice, st));
+  launchUnpackBGRA(st, dRaw.as<uint8_t>(), channels, w, h, dS.as<uchar4>());
+  launchOffsetWrap(st, dS.as<uchar4>(), w, h, offset, dO.as<uchar4>());
+  if (channels == 3) launchPackBGR(st, dO.as<uchar4>(), w, h, w, dOut.as<uint8_t>());
+  S360_CUDA_CHECK(cudaMemcpyAsync(out, channels == 3 ? dOut.p : dO.p, px * channels, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_sharpen(s360_ctx* c, uint8_t* bgr, int w, int h, double sharpening) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(bgr && w > 1 && h > 1, "bad arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer dRaw(px * 3), dS(px * 4), dF(px * 12), dLp(px * 8);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.p, bgr, px * 3, cudaMemcpyHostToDevice, st));
+  launchUnpackBGRA(st, dRaw.as<uint8_t>(), 3, w, h, dS.as<uchar4>());
+  launchSharpen(st, dS.as<uchar4>(), w, h, (float)(1.0f + sharpening), dF.as<float>(), dLp.as<uchar4>());
+  launchPackBGR(st, dS.as<uchar4>(), w, h, w, dRaw.as<uint8_t>());
+  S360_CUDA_CHECK(cudaMemcpyAsync(bgr, dRaw.p, px * 3, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_cubemap(s360_ctx* c, const uint8_t* eye, int w, int h, int fw, int fh, int photo, uint8_t* out) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(eye && out && w > 0 && h > 0 && fw > 0 && fh > 0, "bad arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h, opx = (size_t)6 * fw * fh;
+  DeviceBuffer dRaw(px * 3), dS(px * 4), dO(opx * 3);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.p, eye, px * 3, cudaMemcpyHostToDevice, st));
+  launchUnpackBGRA(st, dRaw.as<uint8_t>(), 3, w, h, dS.as<uchar4>());
+  launchCubemap(st, dS.as<uchar4>(), w, h, fw, fh, photo, dO.as<uint8_t>(), c->rt);
+  S360_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, opx * 3, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_resize_cubic(s360_ctx* c, const uint8_t* src, int w, int h, int channels, int dw, int dh, uint8_t* dst) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(src && dst && w > 0 && h > 0 && dw > 0 && dh > 0 && (channels == 3 || channels == 4), "bad arguments");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h, opx = (size_t)dw * dh;
+  DeviceBuffer dRaw(px * channels), dS(px * 4), dO(opx * 4), dOut(opx * 3);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.p, src, px * channels, cudaMemcpyHostToDevice, st));
+  launchUnpackBGRA(st, dRaw.as<uint8_t>(), channels, w, h, dS.as<uchar4>());
+  if (channels == 3) {
+    launchResizeCubic8(st, dS.as<uchar4>(), w, h, w, 3, nullptr, dw, dh, dw, dOut.as<uint8_t>());
+    S360_CUDA_CHECK(cudaMemcpyAsync(dst, dOut.p, opx * 3, cudaMemcpyDeviceToHost, st));
+  } else {
+    launchResizeCubic8(st, dS.as<uchar4>(), w, h, w, 4, dO.as<uchar4>(), dw, dh, dw, nullptr);
+    S360_CUDA_CHECK(cudaMemcpyAsync(dst, dO.p, opx * 4, cudaMemcpyDeviceToHost, st));
+  }
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+int s360_pole_to_side(s360_ctx* c, const s360_params* p, const uint8_t* side, int sw, int sh, const uint8_t* fish, int fw, int fh,
+                      uint8_t* warpedOut, float* flowOut) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(p && side && fish && warpedOut, "null argument");
+  poleToSide(c, *p, side, sw, sh, fish, fw, fh, warpedOut, flowOut);
+  S360_API_END
+}
+
+// ---- whole frame ----
+int s360_frame_output_size(s360_ctx* c, const s360_params* p, int* eqW, int* eqH, int* cubeW, int* cubeH) {
+  S360_API_BEGIN
+  require(c && p && eqW && eqH && cubeW && cubeH, "null argument");
+  frameOutputSize(c, *p, eqW, eqH, cubeW, cubeH);
+  S360_API_END
+}
+int s360_render_frame(s360_ctx* c, const s360_params* p, const uint8_t* const* images, int w, int h, uint8_t* eq, uint8_t* cube) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(p && images && eq && w > 0 && h > 0, "bad arguments");
+  renderFrameHost(c, *p, images, w, h, eq, cube);
+  S360_API_END
+}
+int s360_render_frame_dev(s360_ctx* c, const s360_params* p, const uint8_t* const* images, int w, int h, uint8_t* eq, uint8_t* cube) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(p && images && eq && w > 0 && h > 0, "bad arguments");
+  renderFrameDevice(c, *p, images, w, h, eq, cube);
+  S360_API_END
+}
+int s360_frame_intermediate(s360_ctx* c, const char* name, int idx, void* out, int* w, int* h, int* ch, int* isFloat) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(name && w && h && ch && isFloat, "null argument");
+  frameIntermediate(c, name, idx, out, w, h, ch, isFloat);
+  S360_API_END
+}
+int s360_frame_stage_ms(s360_ctx* c, float out[7]) {
+  S360_API_BEGIN
+  require(c && out, "null argument");
+  for (int i = 0; i < 7; ++i) out[i] = c->stageMs[i];
+  S360_API_END
+}
+
+// ---- flow files (CvUtil.cpp:159-199): int32 rows, int32 cols, then (f32 x, f32 y) row-major ----
+int s360_flow_save(const char* path, const float* flow, int w, int h) {
+  S360_API_BEGIN
+  require(path && flow && w > 0 && h > 0, "bad arguments");
+  FILE* f = std::fopen(path, "wb");
+  if (!f) throw std::runtime_error(std::string("file not found: ") + path);
+  const int32_t rows = h, cols = w;
+  std::fwrite(&rows, 4, 1, f);
+  std::fwrite(&cols, 4, 1, f);
+  std::fwrite(flow, 8, (size_t)w * h, f);
+  std::fclose(f);
+  S360_API_END
+}
+int s360_flow_load(const char* path, float** out, int* w, int* h) {
+  S360_API_BEGIN
+  require(path && out && w && h, "bad arguments");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) throw std::runtime_error(std::string("file not found: ") + path);
+  int32_t rows = 0, cols = 0;
+  if (std::fread(&rows, 4, 1, f) != 1 || std::fread(&cols, 4, 1, f) != 1 || rows <= 0 || cols <= 0) {
+    std::fclose(f);
+    throw std::runtime_error(std::string("bad flow file: ") + path);
+  }
+  float* buf = (float*)std::malloc((size_t)rows * cols * 8);
+  const size_t got = std::fread(buf, 8, (size_t)rows * cols, f);
+  std::fclose(f);
+  if (got != (size_t)rows * cols) { std::free(buf); throw std::runtime_error(std::string("truncated flow file: ") + path); }
+  *out = buf; *w = cols; *h = rows;
+  S360_API_END
+}
+void s360_free(void* p) { std::free(p); }
+
+}  // extern "C"

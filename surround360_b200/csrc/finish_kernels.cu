@@ -1,0 +1,219 @@
+// sm_100a kernels for alpha feathering, layer flattening and IIR sharpening.
+#include <vector>
+#include "kernels.h"
+
+namespace s360 {
+
+static inline dim3 grid2d(int w, int h, dim3 b) { return dim3(iDivUp(w, b.x), iDivUp(h, b.y)); }
+
+// ------------------------------------------------------------------------------------
+// featherAlphaChannel (CvUtil.cpp:140-157): erode(MORPH_CROSS 2r+1) then GaussianBlur
+// (r x r, sigma r/2) on the 8-bit alpha plane. The blur follows OpenCV's bit-exact 8U
+// path: 8.8 fixed-point taps, BORDER_REFLECT_101, horizontal pass in 16 bits, vertical
+// pass rounded by (v + 2^15) >> 16.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uchar4 readMaybeFlipped(const uchar4* __restrict__ src, int w, int srcH, int flip, int x, int y) {
+  return flip ? __ldg(src + (size_t)(srcH - 1 - y) * w + (w - 1 - x)) : __ldg(src + (size_t)y * w + x);
+}
+__global__ void k_extract_alpha(const uchar4* __restrict__ src, int w, int srcH, int rows, int flip, uint8_t* __restrict__ a) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= rows) return;
+  a[(size_t)y * w + x] = readMaybeFlipped(src, w, srcH, flip, x, y).w;
+}
+__global__ void k_erode_cross(const uint8_t* __restrict__ a, int w, int h, int r, uint8_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  int m = 255;
+  const int y0 = max(y - r, 0), y1 = min(y + r, h - 1);
+  for (int yy = y0; yy <= y1; ++yy) m = min(m, (int)__ldg(a + (size_t)yy * w + x));
+  const int x0 = max(x - r, 0), x1 = min(x + r, w - 1);
+  const uint8_t* row = a + (size_t)y * w;
+  for (int xx = x0; xx <= x1; ++xx) m = min(m, (int)__ldg(row + xx));
+  out[(size_t)y * w + x] = (uint8_t)m;
+}
+__global__ void k_blur8_rows(const uint8_t* __restrict__ a, int w, int h, const int* __restrict__ fk, int n, uint16_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int r = n / 2;
+  const uint8_t* row = a + (size_t)y * w;
+  unsigned s = 0;
+  for (int j = 0; j < n; ++j) s += (unsigned)__ldg(row + reflect101(x + j - r, w)) * (unsigned)__ldg(fk + j);
+  out[(size_t)y * w + x] = (uint16_t)min(s, 65535u);
+}
+// vertical pass + write the feathered alpha next to the (possibly flipped) colours into the
+// 1.2x wrap-extended image: ext(y, x) = cropped(y, x % w) (TRSP:404-411)
+__global__ void k_blur8_cols_extend(const uint16_t* __restrict__ t, int w, int h, const int* __restrict__ fk, int n,
+                                    const uchar4* __restrict__ src, int srcH, int flip, uchar4* __restrict__ ext, int extW) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int r = n / 2;
+  unsigned s = 0;
+  for (int j = 0; j < n; ++j) s += (unsigned)__ldg(t + (size_t)reflect101(y + j - r, h) * w + x) * (unsigned)__ldg(fk + j);
+  uchar4 c = readMaybeFlipped(src, w, srcH, flip, x, y);
+  c.w = (unsigned char)min((s + (1u << 15)) >> 16, 255u);
+  for (int xx = x; xx < extW; xx += w) ext[(size_t)y * extW + xx] = c;
+}
+size_t featherScratchBytes(int w, int rows) { return (size_t)w * rows * 2 + (size_t)w * rows * 2 + 256; }
+void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, int rows, int flip, int erodeSize,
+                         const int* blurKernelFixed, uchar4* extOut, int extW, uint8_t* scratch) {
+  dim3 b(32, 8);
+  const size_t plane = (size_t)w * rows;
+  uint8_t* a0 = scratch;
+  uint8_t* a1 = scratch + plane;
+  uint16_t* t = reinterpret_cast<uint16_t*>(scratch + 2 * plane);
+  k_extract_alpha<<<grid2d(w, rows, b), b, 0, st>>>(src, w, srcH, rows, flip, a0);
+  k_erode_cross<<<grid2d(w, rows, b), b, 0, st>>>(a0, w, rows, erodeSize, a1);
+  k_blur8_rows<<<grid2d(w, rows, b), b, 0, st>>>(a1, w, rows, blurKernelFixed, erodeSize, t);
+  k_blur8_cols_extend<<<grid2d(w, rows, b), b, 0, st>>>(t, w, rows, blurKernelFixed, erodeSize, src, srcH, flip, extOut, extW);
+  g_launchCount += 4;
+}
+void launchFeatherAlpha(cudaStream_t st, const uchar4* src, int w, int h, int erodeSize, const int* blurKernelFixed, uchar4* dst,
+                        uint8_t* scratch) {
+  launchFeatherExtend(st, src, w, h, h, 0, erodeSize, blurKernelFixed, dst, w, scratch);
+}
+__global__ void k_extend_wrap(const uchar4* __restrict__ src, int w, int rows, uchar4* __restrict__ ext, int extW) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= extW || y >= rows) return;
+  ext[(size_t)y * extW + x] = __ldg(src + (size_t)y * w + (x % w));
+}
+void launchExtendWrap(cudaStream_t st, const uchar4* src, int w, int rows, uchar4* extOut, int extW) {
+  dim3 b(32, 8);
+  k_extend_wrap<<<grid2d(extW, rows, b), b, 0, st>>>(src, w, rows, extOut, extW);
+  ++g_launchCount;
+}
+
+// ------------------------------------------------------------------------------------
+// flattenLayersDeghostPreferBase (CvUtil.cpp:224-260)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uchar4 flattenPixel(uchar4 base, uchar4 top) {
+  const float colorDiff =
+      (float)(abs((int)base.x - (int)top.x) + abs((int)base.y - (int)top.y) + abs((int)base.z - (int)top.z)) / 255.0f;
+  const float deghostCoef = tanhf(colorDiff * 5.0f);
+  const float alphaR = (float)top.w / 255.0f;
+  const float alphaL = 1.0f - alphaR;
+  const double expL = exp((double)(5.0f * alphaL * 2.0f));
+  const double expR = exp((double)(5.0f * alphaR));
+  const double sumExp = expL + expR + 0.00001;
+  const float softmaxL = float(expL / sumExp);
+  const float softmaxR = 1.0f - softmaxL;
+  const float wL = lerpf(alphaL, softmaxL, deghostCoef), wR = lerpf(alphaR, softmaxR, deghostCoef);
+  return make_uchar4((unsigned char)truncU8(float(base.x) * wL + float(top.x) * wR),
+                     (unsigned char)truncU8(float(base.y) * wL + float(top.y) * wR),
+                     (unsigned char)truncU8(float(base.z) * wL + float(top.z) * wR), max(top.w, base.w));
+}
+__global__ void k_flatten(const uchar4* __restrict__ base, const uchar4* __restrict__ top, size_t n, uchar4* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = flattenPixel(__ldg(base + i), __ldg(top + i));
+}
+void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out) {
+  const size_t n = (size_t)w * h;
+  k_flatten<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(base, top, n, out);
+  ++g_launchCount;
+}
+// TRSP:864-885: sph = flatten(sph, topWarped); sph = flip(flatten(flip(sph), bottomWarped)).
+// Layers are poleRows tall and zero below (copyMakeBorder, TRSP:538-546).
+__global__ void __launch_bounds__(256)
+k_flatten_poles(const uchar4* __restrict__ base, int w, int h, const uchar4* __restrict__ topLayer, const uchar4* __restrict__ botLayer,
+                int poleRows, uchar4* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  uchar4 v = __ldg(base + (size_t)y * w + x);
+  const uchar4 zero = make_uchar4(0, 0, 0, 0);
+  if (topLayer) v = flattenPixel(v, y < poleRows ? __ldg(topLayer + (size_t)y * w + x) : zero);
+  if (botLayer) {
+    const int fy = h - 1 - y, fx = w - 1 - x;
+    v = flattenPixel(v, fy < poleRows ? __ldg(botLayer + (size_t)fy * w + fx) : zero);
+  }
+  out[(size_t)y * w + x] = v;
+}
+void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const uchar4* topLayer, const uchar4* botLayer,
+                        int poleRows, uchar4* out) {
+  dim3 b(32, 8);
+  k_flatten_poles<<<grid2d(w, h, b), b, 0, st>>>(base, w, h, topLayer, botLayer, poleRows, out);
+  ++g_launchCount;
+}
+
+// ------------------------------------------------------------------------------------
+// sharpen (TRSP:688-696, Filter.h:39-137). The row pass of iirLowPass is run as a column
+// pass on the transposed image so that both passes walk memory with lanes on consecutive
+// addresses: transpose -> columns(wrap) -> transpose -> columns(reflect) -> unsharp.
+// Each recurrence is sequential by definition (one thread per line, 3 channels of ILP);
+// parallelism comes from the 4096..8400 independent lines per eye.
+// ------------------------------------------------------------------------------------
+__global__ void k_transpose4(const uchar4* __restrict__ src, int w, int h, uchar4* __restrict__ dst) {
+  __shared__ uchar4 tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int x = bx + threadIdx.x, y = by + r;
+    if (x < w && y < h) tile[r][threadIdx.x] = src[(size_t)y * w + x];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int y = by + threadIdx.x, x = bx + r;  // dst is h-wide, w-tall
+    if (x < w && y < h) dst[(size_t)x * h + y] = tile[threadIdx.x][r];
+  }
+}
+template <bool WRAP>
+__device__ __forceinline__ int iirBoundary(int i, int n) {
+  if (WRAP) return i < 0 ? n + i : i >= n ? i - n : i;
+  return i < 0 ? -i : i >= n ? 2 * n - i - 2 : i;
+}
+__device__ __forceinline__ float clamp255(float v) { return v < 0.0f ? 0.0f : v > 255.0f ? 255.0f : v; }
+// in/out: w columns, n rows (line length n along y). buf: 3 planes of [n][w] floats.
+template <bool WRAP>
+__global__ void __launch_bounds__(128)
+k_iir_columns(const uchar4* __restrict__ in, int w, int n, float alpha, float* __restrict__ buf, uchar4* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const size_t plane = (size_t)w * n;
+  const float om = 1.0f - alpha;
+  uchar4 p0 = in[x];
+  float v0 = (float)p0.x, v1 = (float)p0.y, v2 = (float)p0.z;
+  for (int j = 1; j <= n; ++j) {  // causal
+    const uchar4 ip = in[(size_t)iirBoundary<WRAP>(j, n) * w + x];
+    v0 = (float)ip.x * om + v0 * alpha;
+    v1 = (float)ip.y * om + v1 * alpha;
+    v2 = (float)ip.z * om + v2 * alpha;
+    const size_t o = (size_t)iirBoundary<WRAP>(j - 1, n) * w + x;
+    buf[o] = v0; buf[plane + o] = v1; buf[2 * plane + o] = v2;
+  }
+  for (int j = n - 2; j >= -1; --j) {  // anticausal
+    const size_t o = (size_t)iirBoundary<WRAP>(j, n) * w + x;
+    v0 = buf[o] * om + v0 * alpha;
+    v1 = buf[plane + o] * om + v1 * alpha;
+    v2 = buf[2 * plane + o] * om + v2 * alpha;
+    out[(size_t)(j + 1) * w + x] =
+        make_uchar4((unsigned char)truncU8(clamp255(v0)), (unsigned char)truncU8(clamp255(v1)), (unsigned char)truncU8(clamp255(v2)), 255);
+  }
+}
+__global__ void k_unsharp(uchar4* __restrict__ img, const uchar4* __restrict__ lp, size_t n, float amount) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uchar4 p = img[i];
+  const uchar4 l = lp[i];
+  auto one = [&](unsigned char pc, unsigned char lc) {
+    const float lf = (float)lc;
+    const float hp = (float)pc - lf;
+    const float ng = 1.0f - expf(-((hp * hp) * 100.0f));
+    return (unsigned char)truncU8(clamp255(lf + hp * ng * amount));
+  };
+  p.x = one(p.x, l.x); p.y = one(p.y, l.y); p.z = one(p.z, l.z);
+  img[i] = p;
+}
+void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, float amount, float* scratchF, uchar4* scratchLp) {
+  // scratchLp holds two w*h uchar4 planes
+  uchar4* tA = scratchLp;
+  uchar4* tB = scratchLp + (size_t)w * h;
+  const float alpha = powf(0.25f, 1.0f / 4.0f);
+  dim3 tb(32, 8);
+  k_transpose4<<<dim3(iDivUp(w, 32), iDivUp(h, 32)), tb, 0, st>>>(img, w, h, tA);                  // tA: h wide, w tall
+  k_iir_columns<true><<<iDivUp(h, 128), 128, 0, st>>>(tA, h, w, alpha, scratchF, tB);               // horizontal pass (wrap)
+  k_transpose4<<<dim3(iDivUp(h, 32), iDivUp(w, 32)), tb, 0, st>>>(tB, h, w, tA);                  // tA: w wide, h tall
+  k_iir_columns<false><<<iDivUp(w, 128), 128, 0, st>>>(tA, w, h, alpha, scratchF, tB);              // vertical pass (reflect)
+  const size_t n = (size_t)w * h;
+  k_unsharp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, tB, n, amount);
+  g_launchCount += 5;
+}
+
+}  // namespace s360

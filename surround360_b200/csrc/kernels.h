@@ -1,0 +1,158 @@
+// Internal launcher API of the sm_100a kernels (host-callable, all asynchronous on `st`).
+// Device images are BGRA8 (uchar4) with a pitch in pixels; flows are float2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "common.cuh"
+#include "remap.cuh"
+
+namespace s360 {
+
+// global launch counter (bench.py "gpu_launches")
+extern unsigned long long g_launchCount;
+
+// ---------------- warp_kernels.cu ----------------
+// BGR8/BGRA8 host-layout source -> BGRA8 with alpha 255 (or source alpha) and the
+// projectSideToSpherical ramp on the first/last `feather` rows (TRSP:110-125).
+void launchPrepSource(cudaStream_t st, const uint8_t* src, int srcChannels, int w, int h, int feather, uchar4* dst);
+
+struct SphericalTables {  // per-destination-column / per-row trig, made on the host with
+  const float* cosX;      // cosf/sinf exactly as ImageWarper.cpp:154-163 evaluates them
+  const float* sinX;
+  const float* cosY;
+  const float* sinY;
+};
+// bicubicRemapToSpherical. poleMode 0: keep remapped alpha (side cameras). poleMode 1:
+// alpha = 255 then the std_alpha_feather ramp of TRSP:629-637 / 671-678 from row featherStart.
+void launchProjectSpherical(cudaStream_t st, const uchar4* src, int sw, int sh, const DevCamera& cam,
+                            const SphericalTables& tb, uchar4* dst, int dw, int dh, int dstPitch, int poleMode,
+                            int featherStart, int featherSize, const RemapTables& rt);
+
+struct NovelViewArgs {
+  const uchar4* proj;     // all side projections, [numCams][camH][camW]
+  const float2* flowLR;   // [numCams][camH][overlapW]
+  const float2* flowRL;
+  int numCams, camW, camH, overlapW, numNovel, bufW;
+  float slabDisp, shiftPx;
+  uchar4* panoL;          // eqrW x eqrH, rows [padAbove, padAbove+camH) written
+  uchar4* panoR;
+  int eqrW, padAbove;
+};
+// renderLazyNovelView x4 + combineLazyViews x2 + stackHorizontal + offsetHorizontalWrap
+// (NovelView.cpp:101-268, TRSP:259-292,380-384) in one pass, both eyes.
+void launchNovelView(cudaStream_t st, const NovelViewArgs& a, const RemapTables& rt);
+
+// One camera pair, chunk-local output (C-ABI s360_novel_view_chunk).
+void launchNovelViewChunk(cudaStream_t st, const uchar4* ovL, const uchar4* ovR, int pitch, const float2* flowLR,
+                          const float2* flowRL, int w, int h, int bufW, int camW, int numNovel, float slabDisp,
+                          uchar4* chunkL, uchar4* chunkR, const RemapTables& rt);
+
+void launchOffsetWrap(cudaStream_t st, const uchar4* src, int w, int h, float offset, uchar4* dst);
+
+struct PoleWarpArgs {  // TRSP:454-546
+  const uchar4* extFish;  // extW x rows
+  const float2* flow;     // extW x rows
+  int cols, rows, extW;
+  float poleCameraRadiusDeg, phiRampStart, phiMid, phiRampEnd;
+  uchar4* warped;         // cols x rows
+};
+void launchPoleWarp(cudaStream_t st, const PoleWarpArgs& a, const RemapTables& rt);
+
+// cv::resize INTER_CUBIC for 8U with `cn` (3 or 4) channel semantics on BGRA storage.
+// If dstPacked3 != nullptr the result is written as packed BGR8 rows (pitch dstW*3 bytes).
+void launchResizeCubic8(cudaStream_t st, const uchar4* src, int sw, int sh, int spitch, int cn, uchar4* dst, int dw, int dh,
+                        int dpitch, uint8_t* dstPacked3);
+
+// convertSphericalToCubemapBicubicRemap + stackOutputCubemapFaces for one eye, packed BGR out.
+void launchCubemap(cudaStream_t st, const uchar4* eye, int w, int h, int faceW, int faceH, int photo, uint8_t* outPacked3,
+                   const RemapTables& rt);
+
+void launchPackBGR(cudaStream_t st, const uchar4* src, int w, int h, int pitch, uint8_t* dst);
+void launchUnpackBGRA(cudaStream_t st, const uint8_t* src, int channels, int w, int h, uchar4* dst);  // alpha=255 if 3ch
+void launchPackBGRA(cudaStream_t st, const uchar4* src, int w, int h, int pitch, uint8_t* dst);
+
+// ---------------- finish_kernels.cu ----------------
+// featherAlphaChannel on a crop of `rows` rows, optionally read through flip(-1) of a
+// srcH-row image, written into a 1.2x wrap-extended image (TRSP:396-411). scratch: 3*w*rows bytes + 2*w*rows u16
+void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, int rows, int flip, int erodeSize,
+                         const int* blurKernelFixed, uchar4* extOut, int extW, uint8_t* scratch);
+void launchExtendWrap(cudaStream_t st, const uchar4* src, int w, int rows, uchar4* extOut, int extW);
+// plain featherAlphaChannel (C-ABI)
+void launchFeatherAlpha(cudaStream_t st, const uchar4* src, int w, int h, int erodeSize, const int* blurKernelFixed,
+                        uchar4* dst, uint8_t* scratch);
+size_t featherScratchBytes(int w, int rows);
+
+// flattenLayersDeghostPreferBase; top may be smaller (topRows) -> zero layer below it.
+// Fused frame variant: base, then top layer, then bottom layer through flip(-1) (TRSP:864-885).
+void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out);
+void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const uchar4* topLayer, const uchar4* botLayer,
+                        int poleRows, uchar4* out);
+
+// sharpenThread: iirLowPass (wrap / reflect) + sharpenWithIirLowPass, in place on BGRA storage.
+// scratch: w*h*3 floats + w*h uchar4
+void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, float amount, float* scratchF, uchar4* scratchLp);
+
+// ---------------- flow_kernels.cu ----------------
+struct FlowParams {  // OpticalFlowFactory.h:25-61
+  float pyrScaleFactor = 0.9f, smoothnessCoef = 0.001f, verticalRegularizationCoef = 0.01f,
+        horizontalRegularizationCoef = 0.01f, gradientStepSize = 0.5f, downscaleFactor = 0.5f;
+  int maxPercentage = 0;
+};
+bool flowParamsByName(const char* name, FlowParams* out);
+
+constexpr int kMaxFlowBatch = 32;
+struct FlowImagePtrs {  // per-flow source views (BGRA8), passed by value to kernels
+  const uchar4* i0[kMaxFlowBatch];
+  const uchar4* i1[kMaxFlowBatch];
+  int pitch0[kMaxFlowBatch];
+  int pitch1[kMaxFlowBatch];
+  int hint[kMaxFlowBatch];
+};
+struct FlowPrevPtrs {  // optional temporal inputs
+  const float2* prevFlow[kMaxFlowBatch];
+  const uchar4* prevI1[kMaxFlowBatch];
+  int prevPitch[kMaxFlowBatch];
+  bool enabled = false;
+};
+
+class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved concurrently
+ public:
+  FlowBatch(int n, int w, int h, const FlowParams& p);
+  ~FlowBatch();
+  FlowBatch(const FlowBatch&) = delete;
+  // flowOut: [n][h][w] float2 contiguous
+  void run(cudaStream_t st, const FlowImagePtrs& imgs, const FlowPrevPtrs& prev, float2* flowOut);
+  int n() const { return n_; }
+  int w() const { return w_; }
+  int h() const { return h_; }
+  size_t bytes() const { return totalBytes_; }
+  int numLevels() const { return (int)lw_.size(); }
+  double levelPixels() const;  // sum over levels of w*h (one flow)
+  // copy the flow as it stands after each level (debug / tests); enabled before run()
+  void enableLevelDump(bool on) { dump_ = on; }
+  const float2* levelDump(int level) const { return dumpBuf_[level]; }
+  int levelW(int l) const { return lw_[l]; }
+  int levelH(int l) const { return lh_[l]; }
+
+ private:
+  struct Impl;
+  int n_, w_, h_, dw_, dh_;
+  FlowParams P_;
+  std::vector<int> lw_, lh_;
+  size_t totalBytes_ = 0;
+  bool dump_ = false;
+  std::vector<float2*> dumpBuf_;
+  // device buffers (per level, batched over n)
+  std::vector<float*> I0_, I1_, A0_, A1_;
+  std::vector<float2*> G0_, G1_, prevPyr_;
+  std::vector<float*> D_, motionPyr_;
+  std::vector<uint8_t*> gate_;
+  uchar4* small0_ = nullptr;
+  uchar4* small1_ = nullptr;
+  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *blurred_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
+  int* progress_ = nullptr;
+  void* arena_ = nullptr;
+};
+
+}  // namespace s360

@@ -1,0 +1,528 @@
+// Per-frame orchestration of the render path on one B200. See pipeline.h.
+#include "pipeline.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace s360 {
+
+void DeviceBuffer::alloc(size_t n) {
+  if (n == 0) n = 256;
+  S360_CUDA_CHECK(cudaMalloc(&p, n));
+  bytes = n;
+}
+void DeviceBuffer::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+// 8.8 fixed-point Gaussian taps of OpenCV's bit-exact 8U GaussianBlur: error-diffusion
+// rounding from the edge inwards, symmetric, centre takes the residual so the taps sum to 256.
+std::vector<int> gaussKernelFixed8(int n, double sigma) {
+  std::vector<double> t(n);
+  double s2 = -0.5 / (sigma * sigma), sum = 0;
+  for (int i = 0; i < n; ++i) { double x = i - (n - 1) * 0.5; t[i] = std::exp(s2 * x * x); sum += t[i]; }
+  std::vector<int> k(n);
+  int isum = 0;
+  double err = 0;
+  for (int i = 0; i < n / 2; ++i) {
+    const double v = t[i] / sum * 256.0 + err;
+    const int q = (int)std::floor(v + 0.5);
+    err = v - q;
+    k[i] = k[n - 1 - i] = q;
+    isum += 2 * q;
+  }
+  k[n / 2] = 256 - isum;
+  return k;
+}
+
+// cv::remap bicubic weight tables (imgwarp.cpp initInterTab2D): 32x32 sub-pixel positions,
+// float products and 15-bit integers whose sum is forced to 2^15.
+static void buildRemapTables(std::vector<short>& wi, std::vector<float>& wf) {
+  wi.assign(1024 * 16, 0);
+  wf.assign(1024 * 16, 0.f);
+  float t1[32][4];
+  for (int k = 0; k < 32; ++k) cubicCoeffs(k * (1.f / 32), t1[k]);
+  for (int yi = 0; yi < 32; ++yi)
+    for (int xi = 0; xi < 32; ++xi) {
+      float* tf = &wf[(size_t)(yi * 32 + xi) * 16];
+      short* ti = &wi[(size_t)(yi * 32 + xi) * 16];
+      int isum = 0;
+      for (int k1 = 0; k1 < 4; ++k1)
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float v = t1[yi][k1] * t1[xi][k2];
+          tf[k1 * 4 + k2] = v;
+          int q = (int)std::nearbyint((double)(v * 32768.f));
+          q = std::min(std::max(q, -32768), 32767);
+          ti[k1 * 4 + k2] = (short)q;
+          isum += q;
+        }
+      if (isum != 32768) {
+        const int diff = isum - 32768;
+        int Mk1 = 2, Mk2 = 2, mk1 = 2, mk2 = 2;
+        for (int k1 = 2; k1 < 4; ++k1)
+          for (int k2 = 2; k2 < 4; ++k2) {
+            if (ti[k1 * 4 + k2] < ti[mk1 * 4 + mk2]) { mk1 = k1; mk2 = k2; }
+            else if (ti[k1 * 4 + k2] > ti[Mk1 * 4 + Mk2]) { Mk1 = k1; Mk2 = k2; }
+          }
+        if (diff < 0) ti[Mk1 * 4 + Mk2] = (short)(ti[Mk1 * 4 + Mk2] - diff);
+        else ti[mk1 * 4 + mk2] = (short)(ti[mk1 * 4 + mk2] - diff);
+      }
+    }
+}
+void initContextTables(s360_ctx* c) {
+  std::vector<short> wi;
+  std::vector<float> wf;
+  buildRemapTables(wi, wf);
+  c->tabI.alloc(wi.size() * 2);
+  c->tabF.alloc(wf.size() * 4);
+  S360_CUDA_CHECK(cudaMemcpy(c->tabI.p, wi.data(), wi.size() * 2, cudaMemcpyHostToDevice));
+  S360_CUDA_CHECK(cudaMemcpy(c->tabF.p, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
+  c->rt.wi = c->tabI.as<short>();
+  c->rt.wf = c->tabF.as<float>();
+}
+
+// ------------------------------------------------------------------------------------
+// geometry: the float/double expression order follows the reference line by line
+// ------------------------------------------------------------------------------------
+Geometry computeGeometry(const Rig& rig, const s360_params& P) {
+  Geometry g{};
+  const int numCams = (int)rig.side.size();
+  const float fovH = rig.approximateFov(false), fovV = rig.approximateFov(true);
+  g.hRadians = 2 * fovH;                                                     // TRSP:155-156
+  g.vRadians = 2 * fovV;
+  g.camH = (int)(P.eqr_height * g.vRadians / M_PI);                           // TRSP:159-162
+  g.camW = (int)(P.eqr_width * g.hRadians / (2 * M_PI));
+  const float camFovDeg = (float)(2 * fovH * (180 / M_PI));                   // TRSP:781-782 -> float param
+  g.fovHRad = (float)(camFovDeg * M_PI / 180.0f);                             // MathUtil.h:32
+  const float overlapDeg = (float)((camFovDeg * float(numCams) - 360.0) / float(numCams));  // TRSP:310-311
+  g.overlapW = (int)(float(g.camW) * (overlapDeg / camFovDeg));               // TRSP:314-315
+  g.numNovel = g.camW - g.overlapW;
+  const float v = atanf((float)(P.zero_parallax_dist / (P.interpupilary_dist / 2.0f)));  // TRSP:340-348
+  const float psi = asinf((float)(sinf(v) * (P.interpupilary_dist / 2.0f) / rig.getRingRadius()));
+  g.slabDisp = psi * (float(g.camW) / g.fovHRad);
+  const float theta = (float)(-M_PI / 2.0f + v + psi);
+  g.shiftPx = (float)(float(P.eqr_width) * (theta / (2.0f * M_PI)));
+  // poles
+  const Camera& bottom = rig.cameras[rig.bottomCamera()];
+  g.poleH = (int)(P.eqr_height * bottom.getFov() / M_PI);                     // TRSP:607-610
+  g.extW = (int)(float(P.eqr_width) * 1.2f);                                  // TRSP:400-401
+  float poleCameraRadius = (float)bottom.getFov();                            // TRSP:461
+  float sideCameraRadius = fovV;                                              // TRSP:464
+  float poleCameraCropRadius = (float)(0.5f * (M_PI / 2 - sideCameraRadius) + 0.5f * (std::min(float(M_PI / 2), poleCameraRadius)));
+  poleCameraCropRadius = (float)(poleCameraCropRadius * (180 / M_PI));
+  poleCameraRadius = (float)(poleCameraRadius * (180 / M_PI));
+  sideCameraRadius = (float)(sideCameraRadius * (180 / M_PI));
+  const float phiFromPole = poleCameraCropRadius, phiFromSide = 90.0f - sideCameraRadius;
+  g.phiMid = (phiFromPole + phiFromSide) / 2.0f;
+  const float phiDiff = fabsf(phiFromPole - phiFromSide);
+  g.phiRampStart = g.phiMid - 1.0f * phiDiff / 2.0f;
+  g.phiRampEnd = g.phiMid + 1.0f * phiDiff / 2.0f;
+  g.poleCameraRadiusDeg = poleCameraRadius;
+  return g;
+}
+
+// trig tables of bicubicRemapToSpherical (ImageWarper.cpp:150-163): float fractions and
+// angles, cosf/sinf on the host -- the per-column / per-row "rig tables" every rank needs.
+static void sphericalTablesHost(int w, int h, float left, float right, float top, float bottom, std::vector<float>& out) {
+  out.resize((size_t)2 * w + 2 * h);
+  for (int x = 0; x < w; ++x) {
+    const float xFrac = (x + 0.5f) / w;
+    const float xAngle = (1 - xFrac) * left + xFrac * right;
+    out[x] = cosf(xAngle);
+    out[w + x] = sinf(xAngle);
+  }
+  for (int y = 0; y < h; ++y) {
+    const float yFrac = (y + 0.5f) / h;
+    const float yAngle = (1 - yFrac) * top + yFrac * bottom;
+    out[2 * w + y] = cosf(yAngle);
+    out[2 * w + h + y] = sinf(yAngle);
+  }
+}
+struct DevSphericalTables {
+  DeviceBuffer buf;
+  SphericalTables t{};
+  void upload(int w, int h, float l, float r, float tp, float b, cudaStream_t st) {
+    std::vector<float> hst;
+    sphericalTablesHost(w, h, l, r, tp, b, hst);
+    buf.ensure(hst.size() * 4);
+    S360_CUDA_CHECK(cudaMemcpyAsync(buf.p, hst.data(), hst.size() * 4, cudaMemcpyHostToDevice, st));
+    S360_CUDA_CHECK(cudaStreamSynchronize(st));
+    float* d = buf.as<float>();
+    t.cosX = d; t.sinX = d + w; t.cosY = d + 2 * w; t.sinY = d + 2 * w + h;
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// frame plan
+// ------------------------------------------------------------------------------------
+struct FramePlan {
+  s360_params P;
+  int imgW = 0, imgH = 0, numCams = 0, nRig = 0;
+  Geometry g;
+  int padAbove = 0;
+  bool top = false, bottom = false;
+  int nPole = 0;  // number of pole flows (2 per enabled pole)
+  std::vector<DevSphericalTables> sideTables;
+  DevSphericalTables topTables, botTables;
+  DeviceBuffer srcRaw;     // staging for host inputs: nRig * imgW*imgH*3
+  DeviceBuffer srcBGRA;    // one prepared source at a time (reused)
+  DeviceBuffer proj;       // [numCams][camH][camW] uchar4
+  DeviceBuffer flowSide;   // [2][numCams][camH][overlapW] float2: LtoR then RtoL
+  DeviceBuffer panoL, panoR;        // eqrW x eqrH uchar4 (pad rows stay zero)
+  DeviceBuffer topSph, botSph;      // eqrW x poleH
+  DeviceBuffer extSide, extFish;    // [nPole][poleH][extW]
+  DeviceBuffer featherScratch;
+  DeviceBuffer poleFlow;            // [nPole][poleH][extW] float2
+  DeviceBuffer poleWarped;          // [nPole][poleH][eqrW]
+  DeviceBuffer eye[2];              // eqrW x eqrH uchar4
+  DeviceBuffer eyePre[2];           // copy before sharpening (keepIntermediates)
+  DeviceBuffer sharpF, sharpLp;
+  DeviceBuffer outEq, outCube;      // device outputs for the host variant
+  std::unique_ptr<FlowBatch> sideFlow, poleFlowBatch;
+  cudaEvent_t ev[8];
+  bool valid = false;
+};
+
+static bool sameParams(const s360_params& a, const s360_params& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
+
+static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
+  if (!c->rigLoaded) throw std::runtime_error("no rig loaded");
+  auto plan = std::make_unique<FramePlan>();
+  FramePlan& F = *plan;
+  F.P = P; F.imgW = imgW; F.imgH = imgH;
+  const Rig& rig = c->rig;
+  F.numCams = (int)rig.side.size();
+  F.nRig = (int)rig.cameras.size();
+  if (P.eqr_width % F.numCams != 0) throw std::runtime_error("eqr_width must be evenly divisible by the number of cameras");
+  F.g = computeGeometry(rig, P);
+  const Geometry& g = F.g;
+  if (g.camH > P.eqr_height || g.camW <= 0 || g.overlapW <= 0 || g.numNovel <= 0) throw std::runtime_error("degenerate side geometry");
+  FlowParams sideFP, poleFP;
+  if (!flowParamsByName(P.side_flow_alg, &sideFP)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + P.side_flow_alg);
+  if (!flowParamsByName(P.polar_flow_alg, &poleFP)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + P.polar_flow_alg);
+  F.padAbove = (P.eqr_height - g.camH) / 2;  // TRSP:702
+  F.top = P.enable_top != 0; F.bottom = P.enable_bottom != 0;
+  F.nPole = (F.top ? 2 : 0) + (F.bottom ? 2 : 0);
+  cudaStream_t st = c->stream;
+  // tables
+  F.sideTables.resize(F.numCams);
+  for (int i = 0; i < F.numCams; ++i) {
+    const float direction = (float)(-float(i) / float(F.numCams) * 2.0f * M_PI);  // TRSP:164
+    F.sideTables[i].upload(g.camW, g.camH, direction + g.hRadians / 2, direction - g.hRadians / 2, g.vRadians / 2, -g.vRadians / 2, st);
+  }
+  if (F.top) {
+    const Camera& cam = rig.cameras[rig.topCamera()];
+    F.topTables.upload(P.eqr_width, g.poleH, (float)(2.0f * M_PI), 0.f, (float)(M_PI / 2.0f), (float)(M_PI / 2.0f - cam.getFov()), st);  // TRSP:660-667
+  }
+  if (F.bottom) {
+    const Camera& cam = rig.cameras[rig.bottomCamera()];
+    F.botTables.upload(P.eqr_width, g.poleH, 0.f, (float)(2.0f * M_PI), (float)(-(M_PI / 2.0f)), (float)(-(M_PI / 2.0f - cam.getFov())), st);  // TRSP:611-618
+  }
+  const size_t eqPx = (size_t)P.eqr_width * P.eqr_height;
+  F.srcRaw.alloc((size_t)F.nRig * imgW * imgH * 3);
+  F.srcBGRA.alloc((size_t)imgW * imgH * 4);
+  F.proj.alloc((size_t)F.numCams * g.camW * g.camH * 4);
+  F.flowSide.alloc((size_t)2 * F.numCams * g.overlapW * g.camH * 8);
+  F.panoL.alloc(eqPx * 4); F.panoR.alloc(eqPx * 4);
+  S360_CUDA_CHECK(cudaMemsetAsync(F.panoL.p, 0, eqPx * 4, st));
+  S360_CUDA_CHECK(cudaMemsetAsync(F.panoR.p, 0, eqPx * 4, st));
+  F.sideFlow = std::make_unique<FlowBatch>(2 * F.numCams, g.overlapW, g.camH, sideFP);
+  if (F.nPole) {
+    if (g.poleH > P.eqr_height) throw std::runtime_error("pole image taller than the equirect");
+    const size_t polePx = (size_t)P.eqr_width * g.poleH, extPx = (size_t)g.extW * g.poleH;
+    F.topSph.alloc(polePx * 4); F.botSph.alloc(polePx * 4);
+    F.extSide.alloc(extPx * 4 * F.nPole); F.extFish.alloc(extPx * 4 * F.nPole);
+    F.featherScratch.alloc(featherScratchBytes(P.eqr_width, g.poleH));
+    F.poleFlow.alloc(extPx * 8 * F.nPole);
+    F.poleWarped.alloc(polePx * 4 * F.nPole);
+    F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP);
+  }
+  for (int e = 0; e < 2; ++e) F.eye[e].alloc(eqPx * 4);
+  if (P.sharpening > 0.0f) { F.sharpF.alloc(eqPx * 3 * 4); F.sharpLp.alloc(eqPx * 4 * 2); }
+  for (auto& e : F.ev) S360_CUDA_CHECK(cudaEventCreate(&e));
+  F.valid = true;
+  c->plan = std::move(plan);
+}
+
+void frameOutputSize(s360_ctx* c, const s360_params& P, int* eqW, int* eqH, int* cubeW, int* cubeH) {
+  (void)c;
+  const bool resize = P.final_eqr_width != 0 && P.final_eqr_height != 0 && P.final_eqr_width != P.eqr_width &&
+                      P.final_eqr_height != P.eqr_height / 2;  // TRSP:938-941
+  *eqW = resize ? P.final_eqr_width : P.eqr_width;
+  *eqH = resize ? (P.final_eqr_height / 2) * 2 : P.eqr_height * 2;
+  const bool cube = P.want_cubemap && P.cubemap_width > 0 && P.cubemap_height > 0;
+  *cubeW = !cube ? 0 : (P.cubemap_photo ? P.cubemap_width : 3 * P.cubemap_width);
+  *cubeH = !cube ? 0 : 2 * (P.cubemap_photo ? 6 * P.cubemap_height : 2 * P.cubemap_height);
+}
+
+void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* imagesDev, int imgW, int imgH, uint8_t* equirectDev,
+                       uint8_t* cubemapDev) {
+  if (!c->plan || !sameParams(c->plan->P, P) || c->plan->imgW != imgW || c->plan->imgH != imgH) buildPlan(c, P, imgW, imgH);
+  FramePlan& F = *c->plan;
+  const Geometry& g = F.g;
+  const Rig& rig = c->rig;
+  cudaStream_t st = c->stream;
+  const int eqW = P.eqr_width, eqH = P.eqr_height;
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[0], st));
+
+  // ---- projections (TRSP:138-175, 564-685) ----
+  uchar4* proj = F.proj.as<uchar4>();
+  for (int i = 0; i < F.numCams; ++i) {
+    const int ci = rig.side[i];
+    launchPrepSource(st, imagesDev[ci], 3, imgW, imgH, P.side_alpha_feather_size, F.srcBGRA.as<uchar4>());
+    launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, rig.cameras[ci].toDevice(), F.sideTables[i].t,
+                           proj + (size_t)i * g.camW * g.camH, g.camW, g.camH, g.camW, 0, 0, 1, c->rt);
+  }
+  const int featherStart = g.poleH - 1 - P.std_alpha_feather_size;
+  if (F.top) {
+    const int ci = rig.topCamera();
+    launchPrepSource(st, imagesDev[ci], 3, imgW, imgH, 0, F.srcBGRA.as<uchar4>());
+    launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, rig.cameras[ci].toDevice(), F.topTables.t, F.topSph.as<uchar4>(), eqW,
+                           g.poleH, eqW, 1, std::max(featherStart, 0), P.std_alpha_feather_size, c->rt);
+  }
+  if (F.bottom) {
+    const int ci = rig.bottomCamera();
+    launchPrepSource(st, imagesDev[ci], 3, imgW, imgH, 0, F.srcBGRA.as<uchar4>());
+    launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, rig.cameras[ci].toDevice(), F.botTables.t, F.botSph.as<uchar4>(), eqW,
+                           g.poleH, eqW, 1, std::max(featherStart, 0), P.std_alpha_feather_size, c->rt);
+  }
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[1], st));
+
+  // ---- side optical flow (TRSP:318-337, NovelView.cpp:270-299) ----
+  {
+    FlowImagePtrs ip{};
+    FlowPrevPtrs pv{};
+    for (int i = 0; i < F.numCams; ++i) {
+      const int r = (i + 1) % F.numCams;
+      const uchar4* ovL = proj + (size_t)i * g.camW * g.camH + (g.camW - g.overlapW);
+      const uchar4* ovR = proj + (size_t)r * g.camW * g.camH;
+      ip.i0[i] = ovL; ip.i1[i] = ovR; ip.hint[i] = S360_HINT_LEFT;                           // flowLtoR
+      ip.i0[F.numCams + i] = ovR; ip.i1[F.numCams + i] = ovL; ip.hint[F.numCams + i] = S360_HINT_RIGHT;  // flowRtoL
+      ip.pitch0[i] = ip.pitch1[i] = ip.pitch0[F.numCams + i] = ip.pitch1[F.numCams + i] = g.camW;
+    }
+    F.sideFlow->run(st, ip, pv, F.flowSide.as<float2>());
+  }
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[2], st));
+
+  // ---- novel views -> eye panoramas (TRSP:339-385, 806-807) ----
+  {
+    NovelViewArgs a{};
+    a.proj = proj;
+    a.flowLR = F.flowSide.as<float2>();
+    a.flowRL = F.flowSide.as<float2>() + (size_t)F.numCams * g.overlapW * g.camH;
+    a.numCams = F.numCams; a.camW = g.camW; a.camH = g.camH; a.overlapW = g.overlapW; a.numNovel = g.numNovel;
+    a.bufW = eqW / F.numCams; a.slabDisp = g.slabDisp; a.shiftPx = g.shiftPx;
+    a.panoL = F.panoL.as<uchar4>(); a.panoR = F.panoR.as<uchar4>(); a.eqrW = eqW; a.padAbove = F.padAbove;
+    launchNovelView(st, a, c->rt);
+  }
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[3], st));
+
+  // ---- poles (TRSP:811-885, 388-561) ----
+  const uchar4* topLayer[2] = {nullptr, nullptr};
+  const uchar4* botLayer[2] = {nullptr, nullptr};
+  if (F.nPole) {
+    const size_t extPx = (size_t)g.extW * g.poleH, polePx = (size_t)eqW * g.poleH;
+    const int* fk = c->blurKernelFor(P.std_alpha_feather_size);
+    FlowImagePtrs ip{};
+    FlowPrevPtrs pv{};
+    int k = 0;
+    struct Slot { bool isTop; int eye; };
+    std::vector<Slot> slots;
+    if (F.top) { slots.push_back({true, 0}); slots.push_back({true, 1}); }
+    if (F.bottom) { slots.push_back({false, 0}); slots.push_back({false, 1}); }
+    for (const Slot& s : slots) {
+      const uchar4* pano = s.eye == 0 ? F.panoL.as<uchar4>() : F.panoR.as<uchar4>();
+      uchar4* extSide = F.extSide.as<uchar4>() + (size_t)k * extPx;
+      uchar4* extFish = F.extFish.as<uchar4>() + (size_t)k * extPx;
+      // crop to the pole rows (of the flipped panorama for the bottom), feather, wrap-extend
+      launchFeatherExtend(st, pano, eqW, eqH, g.poleH, s.isTop ? 0 : 1, P.std_alpha_feather_size, fk, extSide, g.extW,
+                          F.featherScratch.as<uint8_t>());
+      launchExtendWrap(st, s.isTop ? F.topSph.as<uchar4>() : F.botSph.as<uchar4>(), eqW, g.poleH, extFish, g.extW);
+      ip.i0[k] = extSide; ip.i1[k] = extFish; ip.pitch0[k] = ip.pitch1[k] = g.extW; ip.hint[k] = S360_HINT_DOWN;
+      ++k;
+    }
+    F.poleFlowBatch->run(st, ip, pv, F.poleFlow.as<float2>());
+    k = 0;
+    for (const Slot& s : slots) {
+      PoleWarpArgs a{};
+      a.extFish = F.extFish.as<uchar4>() + (size_t)k * extPx;
+      a.flow = F.poleFlow.as<float2>() + (size_t)k * extPx;
+      a.cols = eqW; a.rows = g.poleH; a.extW = g.extW;
+      a.poleCameraRadiusDeg = g.poleCameraRadiusDeg; a.phiRampStart = g.phiRampStart; a.phiMid = g.phiMid; a.phiRampEnd = g.phiRampEnd;
+      a.warped = F.poleWarped.as<uchar4>() + (size_t)k * polePx;
+      launchPoleWarp(st, a, c->rt);
+      (s.isTop ? topLayer : botLayer)[s.eye] = a.warped;
+      ++k;
+    }
+  }
+  // flatten (or plain copy when no poles): eye = BGRA panorama with the pole layers merged
+  launchFlattenPoles(st, F.panoL.as<uchar4>(), eqW, eqH, topLayer[0], botLayer[0], g.poleH, F.eye[0].as<uchar4>());
+  launchFlattenPoles(st, F.panoR.as<uchar4>(), eqW, eqH, topLayer[1], botLayer[1], g.poleH, F.eye[1].as<uchar4>());
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[4], st));
+
+  // ---- sharpen (TRSP:901-913) ----
+  if (c->keepIntermediates)
+    for (int e = 0; e < 2; ++e) {
+      F.eyePre[e].ensure((size_t)eqW * eqH * 4);
+      S360_CUDA_CHECK(cudaMemcpyAsync(F.eyePre[e].p, F.eye[e].p, (size_t)eqW * eqH * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  if (P.sharpening > 0.0f)
+    for (int e = 0; e < 2; ++e)
+      launchSharpen(st, F.eye[e].as<uchar4>(), eqW, eqH, (float)(1.0f + P.sharpening), F.sharpF.as<float>(), F.sharpLp.as<uchar4>());
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[5], st));
+
+  // ---- cubemap + final equirect (TRSP:915-961) ----
+  int oW, oH, cW, cH;
+  frameOutputSize(c, P, &oW, &oH, &cW, &cH);
+  if (cW > 0 && cubemapDev)
+    for (int e = 0; e < 2; ++e)
+      launchCubemap(st, F.eye[e].as<uchar4>(), eqW, eqH, P.cubemap_width, P.cubemap_height, P.cubemap_photo,
+                    cubemapDev + (size_t)e * cW * (cH / 2) * 3, c->rt);
+  for (int e = 0; e < 2; ++e) {
+    uint8_t* dst = equirectDev + (size_t)e * oW * (oH / 2) * 3;
+    if (oW != eqW || oH / 2 != eqH) launchResizeCubic8(st, F.eye[e].as<uchar4>(), eqW, eqH, eqW, 3, nullptr, oW, oH / 2, oW, dst);
+    else launchPackBGR(st, F.eye[e].as<uchar4>(), eqW, eqH, eqW, dst);
+  }
+  S360_CUDA_CHECK(cudaEventRecord(F.ev[6], st));
+}
+
+void renderFrameHost(s360_ctx* c, const s360_params& P, const uint8_t* const* images, int imgW, int imgH, uint8_t* equirect,
+                     uint8_t* cubemap) {
+  if (!c->plan || !sameParams(c->plan->P, P) || c->plan->imgW != imgW || c->plan->imgH != imgH) buildPlan(c, P, imgW, imgH);
+  FramePlan& F = *c->plan;
+  cudaStream_t st = c->stream;
+  const size_t imgBytes = (size_t)imgW * imgH * 3;
+  std::vector<const uint8_t*> dev(F.nRig);
+  for (int i = 0; i < F.nRig; ++i) {
+    uint8_t* d = F.srcRaw.as<uint8_t>() + (size_t)i * imgBytes;
+    dev[i] = d;
+    if (images[i]) S360_CUDA_CHECK(cudaMemcpyAsync(d, images[i], imgBytes, cudaMemcpyHostToDevice, st));
+  }
+  int oW, oH, cW, cH;
+  frameOutputSize(c, P, &oW, &oH, &cW, &cH);
+  F.outEq.ensure((size_t)oW * oH * 3);
+  if (cW > 0 && cubemap) F.outCube.ensure((size_t)cW * cH * 3);
+  renderFrameDevice(c, P, dev.data(), imgW, imgH, F.outEq.as<uint8_t>(), (cW > 0 && cubemap) ? F.outCube.as<uint8_t>() : nullptr);
+  S360_CUDA_CHECK(cudaMemcpyAsync(equirect, F.outEq.p, (size_t)oW * oH * 3, cudaMemcpyDeviceToHost, st));
+  if (cW > 0 && cubemap) S360_CUDA_CHECK(cudaMemcpyAsync(cubemap, F.outCube.p, (size_t)cW * cH * 3, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  // stage times of this frame
+  FramePlan& G = *c->plan;
+  float ms;
+  S360_CUDA_CHECK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[6])); c->stageMs[0] = ms;
+  for (int i = 0; i < 6; ++i) { S360_CUDA_CHECK(cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1])); c->stageMs[i + 1] = ms; }
+}
+
+// ------------------------------------------------------------------------------------
+// intermediates for stage-wise parity tests
+// ------------------------------------------------------------------------------------
+int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w, int* h, int* ch, int* isFloat) {
+  if (!c->plan || !c->plan->valid) throw std::runtime_error("no frame has been rendered on this context");
+  FramePlan& F = *c->plan;
+  const Geometry& g = F.g;
+  const std::string n = name;
+  cudaStream_t st = c->stream;
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int eqW = F.P.eqr_width, eqH = F.P.eqr_height;
+  auto copy2d = [&](const void* src, size_t rowBytes, int rows, size_t srcPitchBytes) {
+    if (out) S360_CUDA_CHECK(cudaMemcpy2D(out, rowBytes, src, srcPitchBytes, rowBytes, rows, cudaMemcpyDeviceToHost));
+  };
+  if (n == "projection") {
+    if (idx < 0 || idx >= F.numCams) throw std::runtime_error("projection index out of range");
+    *w = g.camW; *h = g.camH; *ch = 4; *isFloat = 0;
+    copy2d(F.proj.as<uchar4>() + (size_t)idx * g.camW * g.camH, (size_t)g.camW * 4, g.camH, (size_t)g.camW * 4);
+  } else if (n == "flowLtoR" || n == "flowRtoL") {
+    if (idx < 0 || idx >= F.numCams) throw std::runtime_error("flow index out of range");
+    *w = g.overlapW; *h = g.camH; *ch = 2; *isFloat = 1;
+    const size_t per = (size_t)g.overlapW * g.camH;
+    copy2d(F.flowSide.as<float2>() + ((n == "flowRtoL" ? F.numCams : 0) + idx) * per, (size_t)g.overlapW * 8, g.camH, (size_t)g.overlapW * 8);
+  } else if (n == "panoL" || n == "panoR") {
+    *w = eqW; *h = g.camH; *ch = 4; *isFloat = 0;
+    const uchar4* p = (n == "panoL" ? F.panoL : F.panoR).as<uchar4>() + (size_t)F.padAbove * eqW;
+    copy2d(p, (size_t)eqW * 4, g.camH, (size_t)eqW * 4);
+  } else if (n == "topSpherical" || n == "bottomSpherical") {
+    if (!F.nPole) throw std::runtime_error("poles are not enabled");
+    *w = eqW; *h = g.poleH; *ch = 4; *isFloat = 0;
+    copy2d((n == "topSpherical" ? F.topSph : F.botSph).p, (size_t)eqW * 4, g.poleH, (size_t)eqW * 4);
+  } else if (n == "poleFlow" || n == "poleWarped") {
+    // reference order: top_left, top_right, bottom_left, bottom_right
+    int k = idx;
+    if (!F.top) k -= 2;
+    if (k < 0 || k >= F.nPole) throw std::runtime_error("pole slot not rendered");
+    if (n == "poleFlow") {
+      *w = g.extW; *h = g.poleH; *ch = 2; *isFloat = 1;
+      copy2d(F.poleFlow.as<float2>() + (size_t)k * g.extW * g.poleH, (size_t)g.extW * 8, g.poleH, (size_t)g.extW * 8);
+    } else {  // padded to the equirect height like copyMakeBorder (TRSP:538-546)
+      *w = eqW; *h = eqH; *ch = 4; *isFloat = 0;
+      if (out) {
+        std::memset(out, 0, (size_t)eqW * eqH * 4);
+        copy2d(F.poleWarped.as<uchar4>() + (size_t)k * eqW * g.poleH, (size_t)eqW * 4, g.poleH, (size_t)eqW * 4);
+      }
+    }
+  } else if (n == "eyeL" || n == "eyeR") {
+    const int e = n == "eyeL" ? 0 : 1;
+    if (!F.eyePre[e].p) throw std::runtime_error("enable keep_intermediates before rendering");
+    *w = eqW; *h = eqH; *ch = 4; *isFloat = 0;  // BGRA storage; alpha is not part of the reference image
+    copy2d(F.eyePre[e].p, (size_t)eqW * 4, eqH, (size_t)eqW * 4);
+  } else {
+    throw std::runtime_error("unknown intermediate: " + n);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// poleToSideFlowThread as a stand-alone operator (C-ABI)
+// ------------------------------------------------------------------------------------
+void poleToSide(s360_ctx* c, const s360_params& P, const uint8_t* sideHost, int sw, int sh, const uint8_t* fishHost, int fw, int fh,
+                uint8_t* warpedOut, float* flowOut) {
+  if (!c->rigLoaded) throw std::runtime_error("no rig loaded");
+  if (fw != sw || fh > sh) throw std::runtime_error("pole_to_side: fisheye must be as wide as the side panorama and not taller");
+  FlowParams fp;
+  if (!flowParamsByName(P.polar_flow_alg, &fp)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + P.polar_flow_alg);
+  s360_params Pq = P;
+  const Geometry g = computeGeometry(c->rig, Pq);
+  cudaStream_t st = c->stream;
+  const int extW = (int)(float(fw) * 1.2f);
+  const size_t sidePx = (size_t)sw * sh, fishPx = (size_t)fw * fh, extPx = (size_t)extW * fh;
+  DeviceBuffer dSide(sidePx * 4), dFish(fishPx * 4), dExtS(extPx * 4), dExtF(extPx * 4), dScr(featherScratchBytes(fw, fh)), dFlow(extPx * 8),
+      dWarp(sidePx * 4);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dSide.p, sideHost, sidePx * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(dFish.p, fishHost, fishPx * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemsetAsync(dWarp.p, 0, sidePx * 4, st));
+  launchFeatherExtend(st, dSide.as<uchar4>(), sw, sh, fh, 0, P.std_alpha_feather_size, c->blurKernelFor(P.std_alpha_feather_size),
+                      dExtS.as<uchar4>(), extW, dScr.as<uint8_t>());
+  launchExtendWrap(st, dFish.as<uchar4>(), fw, fh, dExtF.as<uchar4>(), extW);
+  FlowBatch fb(1, extW, fh, fp);
+  FlowImagePtrs ip{};
+  FlowPrevPtrs pv{};
+  ip.i0[0] = dExtS.as<uchar4>(); ip.i1[0] = dExtF.as<uchar4>(); ip.pitch0[0] = ip.pitch1[0] = extW; ip.hint[0] = S360_HINT_DOWN;
+  fb.run(st, ip, pv, dFlow.as<float2>());
+  PoleWarpArgs a{};
+  a.extFish = dExtF.as<uchar4>(); a.flow = dFlow.as<float2>(); a.cols = fw; a.rows = fh; a.extW = extW;
+  a.poleCameraRadiusDeg = g.poleCameraRadiusDeg; a.phiRampStart = g.phiRampStart; a.phiMid = g.phiMid; a.phiRampEnd = g.phiRampEnd;
+  a.warped = dWarp.as<uchar4>();  // first fh rows of the sw x sh output
+  launchPoleWarp(st, a, c->rt);
+  S360_CUDA_CHECK(cudaMemcpyAsync(warpedOut, dWarp.p, sidePx * 4, cudaMemcpyDeviceToHost, st));
+  if (flowOut) S360_CUDA_CHECK(cudaMemcpyAsync(flowOut, dFlow.p, extPx * 8, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+}  // namespace s360
+
+namespace s360 { void resetPlan(s360_ctx* c) { c->plan.reset(); } }
+s360_ctx::s360_ctx() {}
+s360_ctx::~s360_ctx() {}
+
+const int* s360_ctx::blurKernelFor(int erodeSize) {
+  auto it = blurKernels.find(erodeSize);
+  if (it == blurKernels.end()) {
+    if (erodeSize < 1 || (erodeSize & 1) == 0) throw std::runtime_error("std_alpha_feather_size must be odd");
+    std::vector<int> k = s360::gaussKernelFixed8(erodeSize, erodeSize / 2.0f);
+    auto buf = std::make_unique<s360::DeviceBuffer>(k.size() * 4);
+    S360_CUDA_CHECK(cudaMemcpy(buf->p, k.data(), k.size() * 4, cudaMemcpyHostToDevice));
+    it = blurKernels.emplace(erodeSize, std::move(buf)).first;
+  }
+  return it->second->as<int>();
+}

@@ -1,0 +1,71 @@
+// Context and per-frame orchestration (host C++). Mirrors renderStereoPanorama()
+// (surround360_render/source/test/TestRenderStereoPanorama.cpp:716-972) stage by stage,
+// enqueueing the sm_100a kernels on the context's stream. No CPU fallback anywhere.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/s360.h"
+#include "kernels.h"
+#include "rig.h"
+
+namespace s360 {
+
+struct DeviceBuffer {  // RAII cudaMalloc
+  void* p = nullptr;
+  size_t bytes = 0;
+  DeviceBuffer() {}
+  explicit DeviceBuffer(size_t n) { alloc(n); }
+  ~DeviceBuffer() { release(); }
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  DeviceBuffer(DeviceBuffer&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  void alloc(size_t n);
+  void ensure(size_t n) { if (n > bytes) { release(); alloc(n); } }
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Geometry {  // TRSP:155-162, 309-316, 340-348, 607-610
+  int camW, camH, overlapW, numNovel, poleH, extW;
+  float hRadians, vRadians, fovHRad, slabDisp, shiftPx;
+  // pole ramp constants, TRSP:455-481
+  float poleCameraRadiusDeg, phiRampStart, phiMid, phiRampEnd;
+};
+Geometry computeGeometry(const Rig& rig, const s360_params& p);
+
+struct FramePlan;  // all device buffers and tables for one (params, image size)
+
+}  // namespace s360
+
+struct s360_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  s360::Rig rig;
+  bool rigLoaded = false;
+  s360::DeviceBuffer tabI, tabF;        // cv::remap weight tables
+  s360::RemapTables rt{};
+  std::map<int, std::unique_ptr<s360::DeviceBuffer>> blurKernels;  // erodeSize -> 8.8 fixed-point taps
+  std::unique_ptr<s360::FramePlan> plan;
+  bool keepIntermediates = false;
+  float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
+  std::string idScratch;
+
+  const int* blurKernelFor(int erodeSize);
+  s360_ctx();
+  ~s360_ctx();
+};
+
+namespace s360 {
+void frameOutputSize(s360_ctx* c, const s360_params& p, int* eqW, int* eqH, int* cubeW, int* cubeH);
+// images: device BGR8 pointers (one per rig camera); outputs device packed BGR
+void renderFrameDevice(s360_ctx* c, const s360_params& p, const uint8_t* const* imagesDev, int imgW, int imgH,
+                       uint8_t* equirectDev, uint8_t* cubemapDev);
+void renderFrameHost(s360_ctx* c, const s360_params& p, const uint8_t* const* images, int imgW, int imgH, uint8_t* equirect,
+                     uint8_t* cubemap);
+int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w, int* h, int* ch, int* isFloat);
+void poleToSide(s360_ctx* c, const s360_params& p, const uint8_t* sideHost, int sw, int sh, const uint8_t* fishHost, int fw, int fh,
+                uint8_t* warpedOut, float* flowOut);
+std::vector<int> gaussKernelFixed8(int n, double sigma);
+}  // namespace s360
