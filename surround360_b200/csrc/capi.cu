@@ -267,7 +267,7 @@ int s360_flatten_deghost(s360_ctx* c, const uint8_t* base, const uint8_t* top, i
   DeviceBuffer dB(px * 4), dT(px * 4), dO(px * 4);
   S360_CUDA_CHECK(cudaMemcpyAsync(dB.p, base, px * 4, cudaMemcpyHostToDevice, st));
   S360_CUDA_CHECK(cudaMemcpyAsync(dT.p, top, px * 4, cudaMemcpyHostToDevice, st));
-  launchFlatten(st, dB.as<uchar4>(), dT.as<uchar4>(), w, h, dO.as<uchar4>());
+  launchFlatten(st, dB.as<uchar4>(), dT.as<uchar4>(), w, h, dO.as<uchar4>(), c->rt);
   S360_CUDA_CHECK(cudaMemcpyAsync(out, dO.p, px * 4, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
   S360_API_END

@@ -85,52 +85,48 @@ void launchExtendWrap(cudaStream_t st, const uchar4* src, int w, int rows, uchar
 // ------------------------------------------------------------------------------------
 // flattenLayersDeghostPreferBase (CvUtil.cpp:224-260)
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uchar4 flattenPixel(uchar4 base, uchar4 top) {
-  const float colorDiff =
-      (float)(abs((int)base.x - (int)top.x) + abs((int)base.y - (int)top.y) + abs((int)base.z - (int)top.z)) / 255.0f;
-  const float deghostCoef = tanhf(colorDiff * 5.0f);
+__device__ __forceinline__ uchar4 flattenPixel(uchar4 base, uchar4 top, const RemapTables& rt) {
+  const int diffSum = abs((int)base.x - (int)top.x) + abs((int)base.y - (int)top.y) + abs((int)base.z - (int)top.z);
+  const float deghostCoef = __ldg(rt.tanh5 + diffSum);   // tanhf((diffSum / 255.0f) * 5.0f)
   const float alphaR = (float)top.w / 255.0f;
   const float alphaL = 1.0f - alphaR;
-  const double expL = exp((double)(5.0f * alphaL * 2.0f));
-  const double expR = exp((double)(5.0f * alphaR));
-  const double sumExp = expL + expR + 0.00001;
-  const float softmaxL = float(expL / sumExp);
+  const float softmaxL = __ldg(rt.flatSoftL + top.w);    // float(expL / (expL + expR + 1e-5)) in double
   const float softmaxR = 1.0f - softmaxL;
   const float wL = lerpf(alphaL, softmaxL, deghostCoef), wR = lerpf(alphaR, softmaxR, deghostCoef);
   return make_uchar4((unsigned char)truncU8(float(base.x) * wL + float(top.x) * wR),
                      (unsigned char)truncU8(float(base.y) * wL + float(top.y) * wR),
                      (unsigned char)truncU8(float(base.z) * wL + float(top.z) * wR), max(top.w, base.w));
 }
-__global__ void k_flatten(const uchar4* __restrict__ base, const uchar4* __restrict__ top, size_t n, uchar4* __restrict__ out) {
+__global__ void k_flatten(const uchar4* __restrict__ base, const uchar4* __restrict__ top, size_t n, uchar4* __restrict__ out, RemapTables rt) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = flattenPixel(__ldg(base + i), __ldg(top + i));
+  out[i] = flattenPixel(__ldg(base + i), __ldg(top + i), rt);
 }
-void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out) {
+void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out, const RemapTables& rt) {
   const size_t n = (size_t)w * h;
-  k_flatten<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(base, top, n, out);
+  k_flatten<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(base, top, n, out, rt);
   ++g_launchCount;
 }
 // TRSP:864-885: sph = flatten(sph, topWarped); sph = flip(flatten(flip(sph), bottomWarped)).
 // Layers are poleRows tall and zero below (copyMakeBorder, TRSP:538-546).
 __global__ void __launch_bounds__(256)
 k_flatten_poles(const uchar4* __restrict__ base, int w, int h, const uchar4* __restrict__ topLayer, const uchar4* __restrict__ botLayer,
-                int poleRows, uchar4* __restrict__ out) {
+                int poleRows, uchar4* __restrict__ out, RemapTables rt) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
   uchar4 v = __ldg(base + (size_t)y * w + x);
   const uchar4 zero = make_uchar4(0, 0, 0, 0);
-  if (topLayer) v = flattenPixel(v, y < poleRows ? __ldg(topLayer + (size_t)y * w + x) : zero);
+  if (topLayer) v = flattenPixel(v, y < poleRows ? __ldg(topLayer + (size_t)y * w + x) : zero, rt);
   if (botLayer) {
     const int fy = h - 1 - y, fx = w - 1 - x;
-    v = flattenPixel(v, fy < poleRows ? __ldg(botLayer + (size_t)fy * w + fx) : zero);
+    v = flattenPixel(v, fy < poleRows ? __ldg(botLayer + (size_t)fy * w + fx) : zero, rt);
   }
   out[(size_t)y * w + x] = v;
 }
 void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const uchar4* topLayer, const uchar4* botLayer,
-                        int poleRows, uchar4* out) {
+                        int poleRows, uchar4* out, const RemapTables& rt) {
   dim3 b(32, 8);
-  k_flatten_poles<<<grid2d(w, h, b), b, 0, st>>>(base, w, h, topLayer, botLayer, poleRows, out);
+  k_flatten_poles<<<grid2d(w, h, b), b, 0, st>>>(base, w, h, topLayer, botLayer, poleRows, out, rt);
   ++g_launchCount;
 }
 

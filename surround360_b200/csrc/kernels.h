@@ -85,9 +85,9 @@ size_t featherScratchBytes(int w, int rows);
 
 // flattenLayersDeghostPreferBase; top may be smaller (topRows) -> zero layer below it.
 // Fused frame variant: base, then top layer, then bottom layer through flip(-1) (TRSP:864-885).
-void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out);
+void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out, const RemapTables& rt);
 void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const uchar4* topLayer, const uchar4* botLayer,
-                        int poleRows, uchar4* out);
+                        int poleRows, uchar4* out, const RemapTables& rt);
 
 // sharpenThread: iirLowPass (wrap / reflect) + sharpenWithIirLowPass, in place on BGRA storage.
 // scratch: w*h*3 floats + w*h uchar4

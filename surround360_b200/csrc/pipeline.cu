@@ -81,6 +81,26 @@ void initContextTables(s360_ctx* c) {
   S360_CUDA_CHECK(cudaMemcpy(c->tabF.p, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
   c->rt.wi = c->tabI.as<short>();
   c->rt.wf = c->tabF.as<float>();
+  // host libm tables (see RemapTables)
+  std::vector<float> t(766 + 766 + 256);
+  for (int n = 0; n < 766; ++n) {
+    const float colorDiff = (float)n / 255.0f;
+    t[n] = tanhf(colorDiff * 10.0f);
+    t[766 + n] = tanhf(colorDiff * 5.0f);
+  }
+  for (int a = 0; a < 256; ++a) {
+    const float alphaR = (float)a / 255.0f;
+    const float alphaL = 1.0f - alphaR;
+    const double expL = exp(5.0f * alphaL * 2.0f);
+    const double expR = exp(5.0f * alphaR);
+    const double sumExp = expL + expR + 0.00001;
+    t[1532 + a] = float(expL / sumExp);
+  }
+  c->tabT.alloc(t.size() * 4);
+  S360_CUDA_CHECK(cudaMemcpy(c->tabT.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+  c->rt.tanh10 = c->tabT.as<float>();
+  c->rt.tanh5 = c->tabT.as<float>() + 766;
+  c->rt.flatSoftL = c->tabT.as<float>() + 1532;
 }
 
 // ------------------------------------------------------------------------------------
@@ -358,8 +378,8 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
     }
   }
   // flatten (or plain copy when no poles): eye = BGRA panorama with the pole layers merged
-  launchFlattenPoles(st, F.panoL.as<uchar4>(), eqW, eqH, topLayer[0], botLayer[0], g.poleH, F.eye[0].as<uchar4>());
-  launchFlattenPoles(st, F.panoR.as<uchar4>(), eqW, eqH, topLayer[1], botLayer[1], g.poleH, F.eye[1].as<uchar4>());
+  launchFlattenPoles(st, F.panoL.as<uchar4>(), eqW, eqH, topLayer[0], botLayer[0], g.poleH, F.eye[0].as<uchar4>(), c->rt);
+  launchFlattenPoles(st, F.panoR.as<uchar4>(), eqW, eqH, topLayer[1], botLayer[1], g.poleH, F.eye[1].as<uchar4>(), c->rt);
   S360_CUDA_CHECK(cudaEventRecord(F.ev[4], st));
 
   // ---- sharpen (TRSP:901-913) ----

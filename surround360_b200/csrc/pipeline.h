@@ -44,7 +44,7 @@ struct s360_ctx {
   cudaStream_t stream = nullptr;
   s360::Rig rig;
   bool rigLoaded = false;
-  s360::DeviceBuffer tabI, tabF;        // cv::remap weight tables
+  s360::DeviceBuffer tabI, tabF, tabT;  // cv::remap weight tables, libm tables
   s360::RemapTables rt{};
   std::map<int, std::unique_ptr<s360::DeviceBuffer>> blurKernels;  // erodeSize -> 8.8 fixed-point taps
   std::unique_ptr<s360::FramePlan> plan;

@@ -9,9 +9,15 @@
 
 namespace s360 {
 
-struct RemapTables {       // built once per context on the host, resident in HBM (96 KB)
+struct RemapTables {       // built once per context on the host, resident in HBM (~100 KB)
   const short* wi;         // [1024][16]
   const float* wf;         // [1024][16]
+  // Deghost terms whose arguments take few distinct values are tabulated on the host with the
+  // C library the CPU path uses (tanhf/exp are not correctly rounded, and the blends truncate
+  // float->uchar, so a 1-ulp difference would flip pixels whose value sits on an integer):
+  const float* tanh10;     // [766] tanhf((n/255.0f) * 10.0f)   NovelView.cpp:131-138
+  const float* tanh5;      // [766] tanhf((n/255.0f) * 5.0f)    CvUtil.cpp:234-241
+  const float* flatSoftL;  // [256] softmaxL of flattenLayersDeghostPreferBase for top alpha a (CvUtil.cpp:242-248)
 };
 
 enum { BORDER_CONST = 0, BORDER_WRAPPED = 3 };

@@ -121,7 +121,7 @@ __device__ __forceinline__ LazyPix lazySample(const uchar4* __restrict__ img, in
   return r;
 }
 // combineLazyViews for one pixel
-__device__ __forceinline__ uchar4 combineLazy(const LazyPix& L, const LazyPix& R, int imageCols) {
+__device__ __forceinline__ uchar4 combineLazy(const LazyPix& L, const LazyPix& R, int imageCols, const RemapTables& rt) {
   const uchar4 cL = L.c, cR = R.c;
   const unsigned char outAlpha = (float)max(cL.w, cR.w) / 255.0f > 0.1 ? 255 : 0;
   if (cL.w == 0 && cR.w == 0) return make_uchar4(0, 0, 0, outAlpha);
@@ -132,8 +132,8 @@ __device__ __forceinline__ uchar4 combineLazy(const LazyPix& L, const LazyPix& R
   const float norm = blendL + blendR;
   blendL /= norm;
   blendR /= norm;
-  const float colorDiff = (float)(abs((int)cL.x - (int)cR.x) + abs((int)cL.y - (int)cR.y) + abs((int)cL.z - (int)cR.z)) / 255.0f;
-  const float deghostCoef = tanhf(colorDiff * 10.0f);
+  const int diffSum = abs((int)cL.x - (int)cR.x) + abs((int)cL.y - (int)cR.y) + abs((int)cL.z - (int)cR.z);
+  const float deghostCoef = __ldg(rt.tanh10 + diffSum);  // tanhf((diffSum / 255.0f) * 10.0f)
   const double expL = exp((double)(10.0f * blendL) * (1.0 + (double)(20.0f * magL)));
   const double expR = exp((double)(10.0f * blendR) * (1.0 + (double)(20.0f * magR)));
   const double sumExp = expL + expR + 0.00001;
@@ -146,7 +146,7 @@ __device__ __forceinline__ uchar4 combineLazy(const LazyPix& L, const LazyPix& R
 // the chunk column u of pair `pairIdx` for one eye (sign = +1 left eye, -1 right eye)
 __device__ __forceinline__ uchar4 novelPixel(const uchar4* __restrict__ ovL, const uchar4* __restrict__ ovR, int pitch,
                                              const float2* __restrict__ fLR, const float2* __restrict__ fRL, int ovW, int h, int u,
-                                             int v, int camW, int numNovel, float disp, const RemapTables& rt) {
+                                             int v, int camW, int numNovel, int bufW, float disp, const RemapTables& rt) {
   float wx, wy, t;
   if (u < numNovel) {  // TRSP:273-285
     t = float(u) / float(numNovel);
@@ -158,7 +158,7 @@ __device__ __forceinline__ uchar4 novelPixel(const uchar4* __restrict__ ovL, con
   }
   const LazyPix a = lazySample(ovL, pitch, fRL, ovW, h, wx, wy, t, rt);
   const LazyPix b = lazySample(ovR, pitch, fLR, ovW, h, wx, wy, 1.0f - t, rt);
-  return combineLazy(a, b, ovW);
+  return combineLazy(a, b, bufW, rt);  // combineLazyViews normalises by the novel view's width (NovelView.cpp:120-121)
 }
 
 __device__ __forceinline__ int offsetWrapIndex(int x, int cols, float offset) {  // CvUtil.cpp:99-113
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) k_novel_view(NovelViewArgs a, RemapTables
     const uchar4* ovR = a.proj + (size_t)right * a.camW * a.camH;
     const float2* fLR = a.flowLR + (size_t)pair * a.overlapW * a.camH;
     const float2* fRL = a.flowRL + (size_t)pair * a.overlapW * a.camH;
-    const uchar4 c = novelPixel(ovL, ovR, a.camW, fLR, fRL, a.overlapW, a.camH, u, v, a.camW, a.numNovel,
+    const uchar4 c = novelPixel(ovL, ovR, a.camW, fLR, fRL, a.overlapW, a.camH, u, v, a.camW, a.numNovel, a.bufW,
                                 eye == 0 ? a.slabDisp : -a.slabDisp, rt);
     uchar4* pano = eye == 0 ? a.panoL : a.panoR;
     pano[(size_t)(v + a.padAbove) * a.eqrW + X] = c;
@@ -199,8 +199,8 @@ k_novel_chunk(const uchar4* ovL, const uchar4* ovR, int pitch, const float2* fLR
               int numNovel, float slabDisp, uchar4* chunkL, uchar4* chunkR, RemapTables rt) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
   if (u >= bufW || v >= h) return;
-  chunkL[(size_t)v * bufW + u] = novelPixel(ovL, ovR, pitch, fLR, fRL, w, h, u, v, camW, numNovel, slabDisp, rt);
-  chunkR[(size_t)v * bufW + u] = novelPixel(ovL, ovR, pitch, fLR, fRL, w, h, u, v, camW, numNovel, -slabDisp, rt);
+  chunkL[(size_t)v * bufW + u] = novelPixel(ovL, ovR, pitch, fLR, fRL, w, h, u, v, camW, numNovel, bufW, slabDisp, rt);
+  chunkR[(size_t)v * bufW + u] = novelPixel(ovL, ovR, pitch, fLR, fRL, w, h, u, v, camW, numNovel, bufW, -slabDisp, rt);
 }
 void launchNovelViewChunk(cudaStream_t st, const uchar4* ovL, const uchar4* ovR, int pitch, const float2* flowLR, const float2* flowRL,
                           int w, int h, int bufW, int camW, int numNovel, float slabDisp, uchar4* chunkL, uchar4* chunkR,

@@ -68,6 +68,8 @@ if "novel" in which:
     gl, gr = ctx.combineLazyNovelViews(a, b, flr, frl, 200, 600, 200, 60.5)
     ol, orr = ob.novel_view_chunk(a, b, flr, frl, 200, 600, 200, 60.5)
     rep("novel chunk L", gl, ol); rep("novel chunk R", gr, orr)
+    d = gl.astype(int) - ol.astype(int)
+    for ch in range(4): print("  ch", ch, "hist", {int(v): int((d[..., ch] == v).sum()) for v in np.unique(d[..., ch])})
 
 if "frame" in which:
     t = time.time(); frames = synth.render_rig_frames(RIG); print("synth frames", time.time() - t)
