@@ -81,6 +81,14 @@ unsigned long long s360_ctx_launch_count(s360_ctx* ctx);
 /* keep copies of the pre-sharpen eye images for s360_frame_intermediate("eyeL"/"eyeR") */
 int s360_ctx_set_keep_intermediates(s360_ctx* ctx, int on);
 
+/* Profiling of the dominant kernel (the PixFlow wavefront sweep): when enabled, CUDA events
+ * are recorded on the context stream around every sweep launch of s360_render_frame*.
+ * s360_profile_sweep synchronises the stream and returns the accumulated device time (ms),
+ * number of launches, level-pixels processed (flows x width x height per launch) and
+ * wavefront steps since s360_profile_enable(ctx, 1). */
+int s360_profile_enable(s360_ctx* ctx, int on);
+int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, double* level_pixels, double* steps);
+
 /* ---- rig (RIG_JSON.md format) ---- */
 int s360_rig_load_file(s360_ctx* ctx, const char* json_path);
 int s360_rig_load_json(s360_ctx* ctx, const char* json_text);

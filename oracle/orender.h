@@ -177,8 +177,10 @@ static inline Img8 flattenLayersDeghostPreferBase(const Img8& bottom, const Img8
     const float deghostCoef = tanhf(colorDiff * 5.0f);
     const float alphaR = tc[3] / 255.0f;
     const float alphaL = 1.0f - alphaR;
-    const double expL = exp(5.0f * alphaL * 2.0f);
-    const double expR = exp(5.0f * alphaR);
+    // CvUtil.cpp:245-246: the argument is float and CvUtil.cpp is C++ with <math.h> + using
+    // namespace std, so exp() resolves to the float overload (expf), widened to double after
+    const double expL = expf(5.0f * alphaL * 2.0f);
+    const double expR = expf(5.0f * alphaR);
     const double sumExp = expL + expR + 0.00001;
     const float softmaxL = float(expL / sumExp);
     const float softmaxR = 1.0f - softmaxL;

@@ -277,6 +277,14 @@ class Context:
         names = ["total", "projection", "side_flow", "novel_view", "poles", "sharpen", "output"]
         return dict(zip(names, list(o)))
 
+    def profile_enable(self, on=True):
+        _check(lib().s360_profile_enable(self.h, int(on)))
+
+    def profile_sweep(self):
+        ms, n, px, steps = C.c_double(), C.c_ulonglong(), C.c_double(), C.c_double()
+        _check(lib().s360_profile_sweep(self.h, C.byref(ms), C.byref(n), C.byref(px), C.byref(steps)))
+        return dict(ms=ms.value, launches=n.value, level_pixels=px.value, steps=steps.value)
+
     def intermediate(self, name, idx=0):
         w, h, c, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().s360_frame_intermediate(self.h, name.encode(), idx, None, C.byref(w), C.byref(h), C.byref(c), C.byref(f)))

@@ -76,6 +76,24 @@ int s360_ctx_set_keep_intermediates(s360_ctx* c, int on) {
   S360_API_END
 }
 
+int s360_profile_enable(s360_ctx* c, int on) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  c->profile = on != 0;
+  c->sweepProfile = FlowBatch::SweepProfile();
+  S360_API_END
+}
+int s360_profile_sweep(s360_ctx* c, double* ms, unsigned long long* launches, double* levelPixels, double* steps) {
+  S360_API_BEGIN
+  useDevice(c);
+  collectProfile(c);
+  if (ms) *ms = c->sweepProfile.ms;
+  if (launches) *launches = c->sweepProfile.launches;
+  if (levelPixels) *levelPixels = c->sweepProfile.levelPixels;
+  if (steps) *steps = c->sweepProfile.steps;
+  S360_API_END
+}
+
 // ---- rig ----
 int s360_rig_load_json(s360_ctx* c, const char* text) {
   S360_API_BEGIN

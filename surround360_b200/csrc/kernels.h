@@ -134,6 +134,11 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   const float2* levelDump(int level) const { return dumpBuf_[level]; }
   int levelW(int l) const { return lw_[l]; }
   int levelH(int l) const { return lh_[l]; }
+  // sweep-kernel profiling: CUDA events around every k_sweep launch (on the launching stream)
+  struct SweepProfile { double ms = 0, levelPixels = 0, steps = 0; unsigned long long launches = 0; };
+  void enableProfile(bool on) { profile_ = on; }
+  // call after the stream has been synchronised; accumulates and clears pending events
+  void collectProfile(SweepProfile* acc);
 
  private:
   struct Impl;
@@ -142,6 +147,11 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   std::vector<int> lw_, lh_;
   size_t totalBytes_ = 0;
   bool dump_ = false;
+  bool profile_ = false;
+  struct ProfRec { cudaEvent_t a, b; double px, steps; };
+  std::vector<ProfRec> pending_;
+  std::vector<cudaEvent_t> evPool_;
+  cudaEvent_t getEvent();
   std::vector<float2*> dumpBuf_;
   // device buffers (per level, batched over n)
   std::vector<float*> I0_, I1_, A0_, A1_;

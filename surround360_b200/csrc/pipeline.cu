@@ -91,8 +91,8 @@ void initContextTables(s360_ctx* c) {
   for (int a = 0; a < 256; ++a) {
     const float alphaR = (float)a / 255.0f;
     const float alphaL = 1.0f - alphaR;
-    const double expL = exp(5.0f * alphaL * 2.0f);
-    const double expR = exp(5.0f * alphaR);
+    const double expL = expf(5.0f * alphaL * 2.0f);  // float overload in the reference (CvUtil.cpp:245-246)
+    const double expR = expf(5.0f * alphaR);
     const double sumExp = expL + expR + 0.00001;
     t[1532 + a] = float(expL / sumExp);
   }
@@ -286,6 +286,8 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
   cudaStream_t st = c->stream;
   const int eqW = P.eqr_width, eqH = P.eqr_height;
   S360_CUDA_CHECK(cudaEventRecord(F.ev[0], st));
+  F.sideFlow->enableProfile(c->profile);
+  if (F.poleFlowBatch) F.poleFlowBatch->enableProfile(c->profile);
 
   // ---- projections (TRSP:138-175, 564-685) ----
   uchar4* proj = F.proj.as<uchar4>();
@@ -531,7 +533,15 @@ void poleToSide(s360_ctx* c, const s360_params& P, const uint8_t* sideHost, int 
 
 }  // namespace s360
 
-namespace s360 { void resetPlan(s360_ctx* c) { c->plan.reset(); } }
+namespace s360 {
+void resetPlan(s360_ctx* c) { c->plan.reset(); }
+void collectProfile(s360_ctx* c) {
+  if (!c->plan) return;
+  S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->plan->sideFlow) c->plan->sideFlow->collectProfile(&c->sweepProfile);
+  if (c->plan->poleFlowBatch) c->plan->poleFlowBatch->collectProfile(&c->sweepProfile);
+}
+}
 s360_ctx::s360_ctx() {}
 s360_ctx::~s360_ctx() {}
 

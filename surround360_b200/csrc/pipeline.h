@@ -49,6 +49,8 @@ struct s360_ctx {
   std::map<int, std::unique_ptr<s360::DeviceBuffer>> blurKernels;  // erodeSize -> 8.8 fixed-point taps
   std::unique_ptr<s360::FramePlan> plan;
   bool keepIntermediates = false;
+  bool profile = false;
+  s360::FlowBatch::SweepProfile sweepProfile;
   float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   std::string idScratch;
 
@@ -68,4 +70,5 @@ int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w,
 void poleToSide(s360_ctx* c, const s360_params& p, const uint8_t* sideHost, int sw, int sh, const uint8_t* fishHost, int fw, int fh,
                 uint8_t* warpedOut, float* flowOut);
 std::vector<int> gaussKernelFixed8(int n, double sigma);
+void collectProfile(s360_ctx* c);
 }  // namespace s360

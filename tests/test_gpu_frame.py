@@ -1,0 +1,117 @@
+"""Whole-frame parity (s360_render_frame) against the CPU oracle on the 17-camera rig at a
+size the oracle renders in seconds, stage by stage, plus size-independent properties at the
+full 8K configuration."""
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+from surround360_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(eqr_width=2100, eqr_height=1024, final_eqr_width=2048, final_eqr_height=2048, sharpening=0.25, enable_top=1,
+             enable_bottom=1, want_cubemap=1, cubemap_width=256, cubemap_height=256)
+# Stated tolerance of the 8-bit outputs: bit-exact. (Every float op on the path is evaluated in
+# the CPU path's order without FMA, and the libm-dependent deghost terms are host tables.)
+MAX_LSB = 0
+
+
+def close(g, o, what):
+    assert g.shape == o.shape, what
+    d = np.abs(g.astype(np.int32) - o.astype(np.int32)) if g.dtype == np.uint8 else np.abs(g - o)
+    assert d.max() <= MAX_LSB, f"{what}: max diff {d.max()} on {np.count_nonzero(d)} of {d.size}"
+
+
+@pytest.fixture(scope="module")
+def rendered(ctx, orig, frames17):
+    ctx.keep_intermediates(True)
+    eq, cube = ctx.renderStereoPanorama(api.default_params(**SMALL), frames17)
+    ref = orig.render_frame(frames17, ob.make_params(keep_intermediates=1, **SMALL))
+    return eq, cube, ref
+
+
+def test_geometry_matches(ctx, orig):
+    for name in ("3k", "4k", "6k", "8k"):
+        g = ctx.geometry(api.default_params(**api.PRESETS[name]))
+        o = orig.geometry(ob.make_params(**api.PRESETS[name]))
+        assert (g.cam_w, g.cam_h, g.overlap_w, g.num_novel) == (o["camW"], o["camH"], o["overlapW"], o["numNovel"])
+        assert g.slab_disp == o["slabDisp"] and g.shift_px == o["shiftPx"] and g.h_radians == o["hRad"]
+    g = ctx.geometry(api.default_params(**api.PRESETS["8k"]))
+    assert (g.cam_w, g.cam_h, g.overlap_w, g.num_novel, g.pole_h) == (1814, 1769, 1214, 600, 2104)
+
+
+def test_stage_projections(ctx, rendered):
+    for i in range(14):
+        close(ctx.intermediate("projection", i), rendered[2].get("projection", i), f"projection {i}")
+
+
+def test_stage_side_flows(ctx, rendered):
+    for i in range(14):
+        close(ctx.intermediate("flowLtoR", i), rendered[2].get("flowLtoR", i), f"flowLtoR {i}")
+        close(ctx.intermediate("flowRtoL", i), rendered[2].get("flowRtoL", i), f"flowRtoL {i}")
+
+
+def test_stage_panoramas(ctx, rendered):
+    close(ctx.intermediate("panoL"), rendered[2].get("panoL"), "panoL")
+    close(ctx.intermediate("panoR"), rendered[2].get("panoR"), "panoR")
+
+
+def test_stage_poles(ctx, rendered):
+    close(ctx.intermediate("topSpherical"), rendered[2].get("topSpherical"), "topSpherical")
+    close(ctx.intermediate("bottomSpherical"), rendered[2].get("bottomSpherical"), "bottomSpherical")
+    for k in range(4):
+        close(ctx.intermediate("poleFlow", k), rendered[2].get("poleFlow", k), f"poleFlow {k}")
+        close(ctx.intermediate("poleWarped", k), rendered[2].get("poleWarped", k), f"poleWarped {k}")
+
+
+def test_stage_eyes_and_outputs(ctx, rendered):
+    eq, cube, ref = rendered
+    close(ctx.intermediate("eyeL")[..., :3], ref.get("eyeL"), "eyeL")
+    close(ctx.intermediate("eyeR")[..., :3], ref.get("eyeR"), "eyeR")
+    close(eq, ref.get("equirect"), "equirect")
+    close(cube, ref.get("cubemap"), "cubemap")
+
+
+def test_side_only_no_sharpen_no_resize(ctx, orig, frames17):
+    kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1400, final_eqr_height=1400)   # resize guard of TRSP:938-941 -> skipped
+    eq = ctx.renderStereoPanorama(api.default_params(**kw), frames17)
+    ref = orig.render_frame(frames17, ob.make_params(**kw))
+    close(eq, ref.get("equirect"), "equirect (side only)")
+    assert eq.shape == (1400, 1400, 3)
+
+
+def test_top_only_search20(ctx, orig, frames17):
+    kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1024, final_eqr_height=1024, enable_top=1)
+    eq = ctx.renderStereoPanorama(api.default_params(side_flow_alg="pixflow_search_20", polar_flow_alg="pixflow_search_20", **kw), frames17)
+    ref = orig.render_frame(frames17, ob.make_params(side_search20=1, polar_search20=1, **kw))
+    close(eq, ref.get("equirect"), "equirect (top only, search_20)")
+
+
+def test_eqr_width_must_divide_by_cameras(ctx, frames17):
+    with pytest.raises(api.VrCamException, match="evenly divisible"):
+        ctx.renderStereoPanorama(api.default_params(eqr_width=1401, eqr_height=700), frames17)
+
+
+def test_full_8k_properties(frames17):
+    """BASELINE's full size: properties that do not need the (minute-long) CPU render."""
+    c = api.Context(0)
+    from conftest import RIG17
+    c.load_rig(RIG17)
+    p = api.default_params(sharpening=0.25, enable_top=1, enable_bottom=1, **api.PRESETS["8k"])
+    eq1 = c.renderStereoPanorama(p, frames17).copy()
+    eq2 = c.renderStereoPanorama(p, frames17)
+    assert eq1.shape == (8192, 8192, 3)
+    assert np.array_equal(eq1, eq2)                      # deterministic despite the concurrent wavefront bands
+    left, right = eq1[:4096].astype(np.int32), eq1[4096:].astype(np.int32)
+    assert np.abs(left - right).mean() > 0.5             # the two eyes differ (parallax) ...
+    assert np.abs(left - right).mean() < 40              # ... but show the same scene
+    assert eq1.std() > 10
+    # the batched side flows equal the same pairs solved alone through the operator entry point
+    g = c.geometry(p)
+    pa = c.intermediate("projection", 3)
+    pb = c.intermediate("projection", 4)
+    ov_l = np.ascontiguousarray(pa[:, g.cam_w - g.overlap_w:])
+    ov_r = np.ascontiguousarray(pb[:, :g.overlap_w])
+    single = c.computeOpticalFlow("pixflow_low", ov_l, ov_r, hint=api.DirectionHint.LEFT)
+    assert np.array_equal(single, c.intermediate("flowLtoR", 3))
+    c.close()

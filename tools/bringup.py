@@ -91,6 +91,13 @@ if "frame" in which:
         rep(f"poleFlow {k}", ctx.intermediate("poleFlow", k), r.get("poleFlow", k))
         rep(f"poleWarped {k}", ctx.intermediate("poleWarped", k), r.get("poleWarped", k))
     rep("eyeL", ctx.intermediate("eyeL")[..., :3], r.get("eyeL")); rep("eyeR", ctx.intermediate("eyeR")[..., :3], r.get("eyeR"))
+    ge, oe = ctx.intermediate("eyeL")[..., :3], r.get("eyeL")
+    ys, xs, cs = np.nonzero(ge != oe)
+    pl = ctx.intermediate("panoL"); H = ge.shape[0]; padA = (H - pl.shape[0]) // 2
+    tw, bw = r.get("poleWarped", 0), r.get("poleWarped", 2)
+    for y, x, c in list(zip(ys, xs, cs))[:8]:
+        base = pl[y - padA, x] if 0 <= y - padA < pl.shape[0] else np.zeros(4, np.uint8)
+        print("  eyeL diff at", (y, x, c), "gpu", ge[y, x], "oracle", oe[y, x], "base", base, "top", tw[y, x], "bot(flipped idx)", bw[H - 1 - y, ge.shape[1] - 1 - x])
     rep("equirect", eq, r.get("equirect")); rep("cubemap", cube, r.get("cubemap"))
     np.save(os.path.join(ROOT, "gpurun_out", "eq_small_gpu.npy"), eq[::4, ::4])
 print("launches", ctx.launch_count())
