@@ -324,6 +324,44 @@ void launchResizeCubic8(cudaStream_t st, const uchar4* src, int sw, int sh, int 
 // cubemap: ImageWarper.cpp:26-141 + CvUtil.cpp:117-138
 // ------------------------------------------------------------------------------------
 enum { FACE_BACK, FACE_LEFT, FACE_TOP, FACE_BOTTOM, FACE_FRONT, FACE_RIGHT };
+// acosf as the CPU path's C library computes it (fdlibm e_acosf.c rational approximation;
+// only IEEE + - * / sqrt, so with -fmad=false the device result is the same float).
+// tools/check_acosf_port.c verifies this restatement against glibc 2.39 on every float in [-1, 1].
+__device__ __forceinline__ float acosfRef(float x) {
+  const float one = 1.0f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f,
+              pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f,
+              pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f, qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f,
+              qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+  const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+  if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo;
+  if (ix > 0x3f800000) return (x - x) / (x - x);
+  if (ix < 0x3f000000) {
+    if (ix <= 0x32800000) return pio2_hi + pio2_lo;
+    const float z = x * x;
+    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float r = p / q;
+    return pio2_hi - (x - (pio2_lo - x * r));
+  }
+  if (hx < 0) {
+    const float z = (one + x) * 0.5f;
+    const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const float s = sqrtf(z);
+    const float r = p / q;
+    const float w = r * s - pio2_lo;
+    return pi - 2.0f * (s + w);
+  }
+  const float z = (one - x) * 0.5f;
+  const float s = sqrtf(z);
+  const float df = __int_as_float(__float_as_int(s) & 0xfffff000);
+  const float c = (z - df * df) / (s + df);
+  const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+  const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+  const float r = p / q;
+  const float w = r * s + c;
+  return 2.0f * (df + w);
+}
 __device__ __forceinline__ void cubemapCoord(float x, float y, int face, int srcW, int srcH, float fov, float& srcX, float& srcY) {
   float d0 = x, d1 = y, d2 = 0.5f, o0 = x, o1 = y, o2 = 0.5f;
   switch (face) {
@@ -336,8 +374,8 @@ __device__ __forceinline__ void cubemapCoord(float x, float y, int face, int src
   }
   const float r = sqrtf(o0 * o0 + o1 * o1);
   const double nrm = sqrt((double)o0 * o0 + (double)o1 * o1 + (double)o2 * o2);
-  const float phi = acosf((float)((double)o2 / nrm));
-  float theta = r > 0.0f ? acosf(fabsf(o0 / r)) : 0.0f;
+  const float phi = acosfRef((float)((double)o2 / nrm));
+  float theta = r > 0.0f ? acosfRef(fabsf(o0 / r)) : 0.0f;
   const double PI = 3.14159265358979323846;
   if (o0 > 0 && o1 > 0) {}
   else if (o0 <= 0 && o1 > 0) theta = (float)(PI - (double)theta);

@@ -32,13 +32,14 @@ def test_config1_pair_512(ctx, pair, alg, hint):
 
 
 def test_recovers_known_flow(ctx, pair):
-    # I1 = I0 warped by u = 4 + 3 sin(2 pi y/512), v = 1.5 sin(2 pi x/256): flow(I0->I1) ~ (u, v) in the interior
+    # I1(p) = I0(p + d) with d = (4 + 3 sin(2 pi y/512), 1.5 sin(2 pi x/256)); the flow warps I1 to look
+    # like I0 (OpticalFlowInterface.h:26-33): I1(p + f) = I0(p)  =>  f ~ -d in the interior
     i0, i1 = pair
     f = ctx.computeOpticalFlow("pixflow_low", i0, i1, hint=3)
     yy, xx = np.mgrid[64:448, 64:448]
     u = 4 + 3 * np.sin(2 * np.pi * yy / 512)
     v = 1.5 * np.sin(2 * np.pi * xx / 256)
-    err = np.hypot(f[64:448, 64:448, 0] - u, f[64:448, 64:448, 1] - v)
+    err = np.hypot(f[64:448, 64:448, 0] + u, f[64:448, 64:448, 1] + v)
     assert np.median(err) < 0.5
 
 
