@@ -87,6 +87,9 @@ int s360_ctx_set_keep_intermediates(s360_ctx* ctx, int on);
  * number of launches, level-pixels processed (flows x width x height per launch) and
  * wavefront steps since s360_profile_enable(ctx, 1). */
 int s360_profile_enable(s360_ctx* ctx, int on);
+/* Whole-frame CUDA-graph replay (default on). Profiling, keep_intermediates and the stage timers
+ * need the plain launch path and switch it off implicitly for the frames they cover. */
+int s360_ctx_set_graphs(s360_ctx* ctx, int on);
 int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, double* level_pixels, double* steps);
 
 /* ---- rig (RIG_JSON.md format) ---- */

@@ -277,6 +277,9 @@ class Context:
         names = ["total", "projection", "side_flow", "novel_view", "poles", "sharpen", "output"]
         return dict(zip(names, list(o)))
 
+    def set_graphs(self, on=True):
+        _check(lib().s360_ctx_set_graphs(self.h, int(on)))
+
     def profile_enable(self, on=True):
         _check(lib().s360_profile_enable(self.h, int(on)))
 

@@ -76,6 +76,12 @@ int s360_ctx_set_keep_intermediates(s360_ctx* c, int on) {
   S360_API_END
 }
 
+int s360_ctx_set_graphs(s360_ctx* c, int on) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  c->useGraphs = on != 0;
+  S360_API_END
+}
 int s360_profile_enable(s360_ctx* c, int on) {
   S360_API_BEGIN
   require(c != nullptr, "null context");
@@ -249,7 +255,7 @@ int s360_flow_compute(s360_ctx* c, const char* alg, const uint8_t* i0, const uin
     S360_CUDA_CHECK(cudaMemcpyAsync(dP1.p, prevI1, px * 4, cudaMemcpyHostToDevice, st));
     pv.enabled = true; pv.prevFlow[0] = dPF.as<float2>(); pv.prevI1[0] = dP1.as<uchar4>(); pv.prevPitch[0] = w;
   }
-  FlowBatch fb(1, w, h, fp);
+  FlowBatch fb(1, w, h, fp, pv.enabled);
   fb.run(st, ip, pv, dF.as<float2>());
   S360_CUDA_CHECK(cudaMemcpyAsync(flowOut, dF.p, px * 8, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));

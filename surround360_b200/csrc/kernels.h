@@ -118,7 +118,8 @@ struct FlowPrevPtrs {  // optional temporal inputs
 
 class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved concurrently
  public:
-  FlowBatch(int n, int w, int h, const FlowParams& p);
+  // temporal: allocate the previous-flow / motion pyramids; levelDump: allocate per-level dump planes
+  FlowBatch(int n, int w, int h, const FlowParams& p, bool temporal = false, bool levelDump = false);
   ~FlowBatch();
   FlowBatch(const FlowBatch&) = delete;
   // flowOut: [n][h][w] float2 contiguous
@@ -148,6 +149,7 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   size_t totalBytes_ = 0;
   bool dump_ = false;
   bool profile_ = false;
+  bool temporal_ = false, dumpAlloc_ = false;
   struct ProfRec { cudaEvent_t a, b; double px, steps; };
   std::vector<ProfRec> pending_;
   std::vector<cudaEvent_t> evPool_;
@@ -155,12 +157,12 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   std::vector<float2*> dumpBuf_;
   // device buffers (per level, batched over n)
   std::vector<float*> I0_, I1_, A0_, A1_;
-  std::vector<float2*> G0_, G1_, prevPyr_;
+  std::vector<float4*> rowRec_, quad_;
+  std::vector<float2*> prevPyr_;
   std::vector<float*> D_, motionPyr_;
-  std::vector<uint8_t*> gate_;
   uchar4* small0_ = nullptr;
   uchar4* small1_ = nullptr;
-  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *blurred_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
+  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *g1Scratch_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
   void* arena_ = nullptr;
 };

@@ -202,7 +202,11 @@ struct FramePlan {
   DeviceBuffer outEq, outCube;      // device outputs for the host variant
   std::unique_ptr<FlowBatch> sideFlow, poleFlowBatch;
   cudaEvent_t ev[8];
+  cudaGraphExec_t graphExec = nullptr;
+  bool graphHasCube = false, lastWasTimed = false;
+  unsigned long long graphLaunches = 0;
   bool valid = false;
+  ~FramePlan() { if (graphExec) cudaGraphExecDestroy(graphExec); }
 };
 
 static bool sameParams(const s360_params& a, const s360_params& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
@@ -258,6 +262,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
     F.poleFlow.alloc(extPx * 8 * F.nPole);
     F.poleWarped.alloc(polePx * 4 * F.nPole);
     F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP);
+    (void)c->blurKernelFor(P.std_alpha_feather_size);  // allocate now: nothing may allocate while a frame is captured
   }
   for (int e = 0; e < 2; ++e) F.eye[e].alloc(eqPx * 4);
   if (P.sharpening > 0.0f) { F.sharpF.alloc(eqPx * 3 * 4); F.sharpLp.alloc(eqPx * 4 * 2); }
@@ -277,17 +282,20 @@ void frameOutputSize(s360_ctx* c, const s360_params& P, int* eqW, int* eqH, int*
   *cubeH = !cube ? 0 : 2 * (P.cubemap_photo ? 6 * P.cubemap_height : 2 * P.cubemap_height);
 }
 
-void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* imagesDev, int imgW, int imgH, uint8_t* equirectDev,
-                       uint8_t* cubemapDev) {
-  if (!c->plan || !sameParams(c->plan->P, P) || c->plan->imgW != imgW || c->plan->imgH != imgH) buildPlan(c, P, imgW, imgH);
+// Enqueues every kernel of one frame on the context stream. `timed`: record the stage events and
+// the per-sweep profiling events (not possible while the stream is being captured into a graph).
+static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* equirectDev, uint8_t* cubemapDev, bool timed) {
   FramePlan& F = *c->plan;
+  const s360_params& P = F.P;
+  const int imgW = F.imgW, imgH = F.imgH;
   const Geometry& g = F.g;
   const Rig& rig = c->rig;
   cudaStream_t st = c->stream;
   const int eqW = P.eqr_width, eqH = P.eqr_height;
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[0], st));
-  F.sideFlow->enableProfile(c->profile);
-  if (F.poleFlowBatch) F.poleFlowBatch->enableProfile(c->profile);
+  auto stageEvent = [&](int i) { if (timed) S360_CUDA_CHECK(cudaEventRecord(F.ev[i], st)); };
+  stageEvent(0);
+  F.sideFlow->enableProfile(timed && c->profile);
+  if (F.poleFlowBatch) F.poleFlowBatch->enableProfile(timed && c->profile);
 
   // ---- projections (TRSP:138-175, 564-685) ----
   uchar4* proj = F.proj.as<uchar4>();
@@ -310,7 +318,7 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
     launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, rig.cameras[ci].toDevice(), F.botTables.t, F.botSph.as<uchar4>(), eqW,
                            g.poleH, eqW, 1, std::max(featherStart, 0), P.std_alpha_feather_size, c->rt);
   }
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[1], st));
+  stageEvent(1);
 
   // ---- side optical flow (TRSP:318-337, NovelView.cpp:270-299) ----
   {
@@ -326,7 +334,7 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
     }
     F.sideFlow->run(st, ip, pv, F.flowSide.as<float2>());
   }
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[2], st));
+  stageEvent(2);
 
   // ---- novel views -> eye panoramas (TRSP:339-385, 806-807) ----
   {
@@ -339,7 +347,7 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
     a.panoL = F.panoL.as<uchar4>(); a.panoR = F.panoR.as<uchar4>(); a.eqrW = eqW; a.padAbove = F.padAbove;
     launchNovelView(st, a, c->rt);
   }
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[3], st));
+  stageEvent(3);
 
   // ---- poles (TRSP:811-885, 388-561) ----
   const uchar4* topLayer[2] = {nullptr, nullptr};
@@ -382,7 +390,7 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
   // flatten (or plain copy when no poles): eye = BGRA panorama with the pole layers merged
   launchFlattenPoles(st, F.panoL.as<uchar4>(), eqW, eqH, topLayer[0], botLayer[0], g.poleH, F.eye[0].as<uchar4>(), c->rt);
   launchFlattenPoles(st, F.panoR.as<uchar4>(), eqW, eqH, topLayer[1], botLayer[1], g.poleH, F.eye[1].as<uchar4>(), c->rt);
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[4], st));
+  stageEvent(4);
 
   // ---- sharpen (TRSP:901-913) ----
   if (c->keepIntermediates)
@@ -393,7 +401,7 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
   if (P.sharpening > 0.0f)
     for (int e = 0; e < 2; ++e)
       launchSharpen(st, F.eye[e].as<uchar4>(), eqW, eqH, (float)(1.0f + P.sharpening), F.sharpF.as<float>(), F.sharpLp.as<uchar4>());
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[5], st));
+  stageEvent(5);
 
   // ---- cubemap + final equirect (TRSP:915-961) ----
   int oW, oH, cW, cH;
@@ -407,7 +415,66 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
     if (oW != eqW || oH / 2 != eqH) launchResizeCubic8(st, F.eye[e].as<uchar4>(), eqW, eqH, eqW, 3, nullptr, oW, oH / 2, oW, dst);
     else launchPackBGR(st, F.eye[e].as<uchar4>(), eqW, eqH, eqW, dst);
   }
-  S360_CUDA_CHECK(cudaEventRecord(F.ev[6], st));
+  stageEvent(6);
+}
+
+// A frame is ~1000 small launches; replaying it as one CUDA graph removes the host launch cost and
+// the launch-queue back-pressure that otherwise throttles several frames in flight. The graph
+// reads the plan-owned input staging buffer and writes the plan-owned output buffers, so it is
+// captured once per plan; per call only the D2D copies in and out are enqueued around it.
+static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
+  FramePlan& F = *c->plan;
+  cudaStream_t st = c->stream;
+  const size_t imgBytes = (size_t)F.imgW * F.imgH * 3;
+  std::vector<const uint8_t*> dev(F.nRig);
+  for (int i = 0; i < F.nRig; ++i) dev[i] = F.srcRaw.as<uint8_t>() + (size_t)i * imgBytes;
+  uint8_t* cube = wantCube ? F.outCube.as<uint8_t>() : nullptr;
+  const bool useGraph = c->useGraphs && !c->profile && !c->keepIntermediates;
+  if (!useGraph) {
+    enqueueFrame(c, dev.data(), F.outEq.as<uint8_t>(), cube, true);
+    F.lastWasTimed = true;
+    return;
+  }
+  if (!F.graphExec || F.graphHasCube != wantCube) {
+    if (F.graphExec) { cudaGraphExecDestroy(F.graphExec); F.graphExec = nullptr; }
+    const unsigned long long before = g_launchCount;
+    cudaGraph_t graph = nullptr;
+    S360_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueueFrame(c, dev.data(), F.outEq.as<uint8_t>(), cube, false);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    S360_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+    F.graphLaunches = g_launchCount - before;
+    g_launchCount = before;  // nothing has run yet; replays are counted below
+    S360_CUDA_CHECK(cudaGraphInstantiate(&F.graphExec, graph, 0));
+    cudaGraphDestroy(graph);
+    F.graphHasCube = wantCube;
+  }
+  S360_CUDA_CHECK(cudaGraphLaunch(F.graphExec, st));
+  g_launchCount += F.graphLaunches;
+  F.lastWasTimed = false;
+}
+
+void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* imagesDev, int imgW, int imgH, uint8_t* equirectDev,
+                       uint8_t* cubemapDev) {
+  if (!c->plan || !sameParams(c->plan->P, P) || c->plan->imgW != imgW || c->plan->imgH != imgH) buildPlan(c, P, imgW, imgH);
+  FramePlan& F = *c->plan;
+  cudaStream_t st = c->stream;
+  const size_t imgBytes = (size_t)imgW * imgH * 3;
+  for (int i = 0; i < F.nRig; ++i)
+    if (imagesDev[i]) S360_CUDA_CHECK(cudaMemcpyAsync(F.srcRaw.as<uint8_t>() + (size_t)i * imgBytes, imagesDev[i], imgBytes, cudaMemcpyDeviceToDevice, st));
+  int oW, oH, cW, cH;
+  frameOutputSize(c, P, &oW, &oH, &cW, &cH);
+  F.outEq.ensure((size_t)oW * oH * 3);
+  const bool wantCube = cW > 0 && cubemapDev;
+  if (wantCube) F.outCube.ensure((size_t)cW * cH * 3);
+  runFrameFromStaging(c, wantCube);
+  S360_CUDA_CHECK(cudaMemcpyAsync(equirectDev, F.outEq.p, (size_t)oW * oH * 3, cudaMemcpyDeviceToDevice, st));
+  if (wantCube) S360_CUDA_CHECK(cudaMemcpyAsync(cubemapDev, F.outCube.p, (size_t)cW * cH * 3, cudaMemcpyDeviceToDevice, st));
 }
 
 void renderFrameHost(s360_ctx* c, const s360_params& P, const uint8_t* const* images, int imgW, int imgH, uint8_t* equirect,
@@ -416,20 +483,18 @@ void renderFrameHost(s360_ctx* c, const s360_params& P, const uint8_t* const* im
   FramePlan& F = *c->plan;
   cudaStream_t st = c->stream;
   const size_t imgBytes = (size_t)imgW * imgH * 3;
-  std::vector<const uint8_t*> dev(F.nRig);
-  for (int i = 0; i < F.nRig; ++i) {
-    uint8_t* d = F.srcRaw.as<uint8_t>() + (size_t)i * imgBytes;
-    dev[i] = d;
-    if (images[i]) S360_CUDA_CHECK(cudaMemcpyAsync(d, images[i], imgBytes, cudaMemcpyHostToDevice, st));
-  }
+  for (int i = 0; i < F.nRig; ++i)
+    if (images[i]) S360_CUDA_CHECK(cudaMemcpyAsync(F.srcRaw.as<uint8_t>() + (size_t)i * imgBytes, images[i], imgBytes, cudaMemcpyHostToDevice, st));
   int oW, oH, cW, cH;
   frameOutputSize(c, P, &oW, &oH, &cW, &cH);
   F.outEq.ensure((size_t)oW * oH * 3);
-  if (cW > 0 && cubemap) F.outCube.ensure((size_t)cW * cH * 3);
-  renderFrameDevice(c, P, dev.data(), imgW, imgH, F.outEq.as<uint8_t>(), (cW > 0 && cubemap) ? F.outCube.as<uint8_t>() : nullptr);
+  const bool wantCube = cW > 0 && cubemap;
+  if (wantCube) F.outCube.ensure((size_t)cW * cH * 3);
+  runFrameFromStaging(c, wantCube);
   S360_CUDA_CHECK(cudaMemcpyAsync(equirect, F.outEq.p, (size_t)oW * oH * 3, cudaMemcpyDeviceToHost, st));
-  if (cW > 0 && cubemap) S360_CUDA_CHECK(cudaMemcpyAsync(cubemap, F.outCube.p, (size_t)cW * cH * 3, cudaMemcpyDeviceToHost, st));
+  if (wantCube) S360_CUDA_CHECK(cudaMemcpyAsync(cubemap, F.outCube.p, (size_t)cW * cH * 3, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (!F.lastWasTimed) return;   // graph replay: no per-stage events
   // stage times of this frame
   FramePlan& G = *c->plan;
   float ms;

@@ -50,6 +50,7 @@ struct s360_ctx {
   std::unique_ptr<s360::FramePlan> plan;
   bool keepIntermediates = false;
   bool profile = false;
+  bool useGraphs = true;
   s360::FlowBatch::SweepProfile sweepProfile;
   float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   std::string idScratch;
