@@ -115,3 +115,42 @@ def test_full_8k_properties(frames17):
     single = c.computeOpticalFlow("pixflow_low", ov_l, ov_r, hint=api.DirectionHint.LEFT)
     assert np.array_equal(single, c.intermediate("flowLtoR", 3))
     c.close()
+
+
+def test_cli_is_a_drop_in(ctx, frames17, tmp_path, rig_path):
+    """The TestRenderStereoPanorama binary: reference flags in, PNG + flow .bin files out, same pixels
+    as the library call."""
+    import json
+    import os
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "surround360_b200", "bin", "TestRenderStereoPanorama")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    rig = json.load(open(rig_path))
+    imgs = tmp_path / "rgb"
+    for cam, im in zip(rig["cameras"], frames17):
+        (imgs / cam["id"]).mkdir(parents=True)
+        assert cv2.imwrite(str(imgs / cam["id"] / "000000.png"), im)
+    out = tmp_path / "out"
+    (out / "flow" / "000000").mkdir(parents=True)
+    kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1024, final_eqr_height=1024, sharpening=0.25, enable_top=1, enable_bottom=1)
+    cmd = [exe, "--rig_json_file", rig_path, "--imgs_dir", str(imgs), "--frame_number", "000000", "--output_data_dir", str(out),
+           "--prev_frame_data_dir", "NONE", "--output_equirect_path", str(out / "eqr.png"), "--output_cubemap_path", str(out / "cube.png"),
+           "--cubemap_width=128", "--cubemap_height", "128", "--cubemap_format", "photo", "--enable_top", "--enable_bottom=true",
+           "--sharpening", "0.25", "--eqr_width", "1400", "--eqr_height", "700", "--final_eqr_width", "1024", "--final_eqr_height", "1024",
+           "--v", "1", "--logbuflevel", "-1", "--stderrthreshold", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "--- Runtime breakdown (sec) ---" in r.stderr and "Side optical flow:" in r.stderr
+    eq_cli = cv2.imread(str(out / "eqr.png"), cv2.IMREAD_COLOR)
+    cube_cli = cv2.imread(str(out / "cube.png"), cv2.IMREAD_COLOR)
+    eq, cube = ctx.renderStereoPanorama(api.default_params(want_cubemap=1, cubemap_photo=1, cubemap_width=128, cubemap_height=128, **kw), frames17)
+    assert np.array_equal(eq_cli, eq) and np.array_equal(cube_cli, cube)
+    f = api.readFlowFromFile(str(out / "flow" / "000000" / "flowLtoR_3.bin"))
+    assert np.array_equal(f, ctx.intermediate("flowLtoR", 3))
+    assert os.path.exists(out / "flow" / "000000" / "flow_bottom_right.bin")
+    # error behaviour: unknown flow algorithm -> VrCamException text, non-zero exit
+    r = subprocess.run(cmd + ["--side_flow_alg", "nope"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unrecognized flow algorithm name: nope" in r.stderr
