@@ -21,6 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# frames in flight run on separate streams; the default of 8 hardware work queues would serialise them
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np
 
 METRIC = "8k_stereo_equirect_frames_per_sec"
@@ -148,7 +150,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--preset", default="8k", choices=["3k", "4k", "6k", "8k"])
     ap.add_argument("--cubemap", action="store_true", help="config 5: also produce the 1536^2 cubemap strip")
-    ap.add_argument("--inflight", type=int, default=4, help="frames in flight per GPU (contexts/streams)")
+    ap.add_argument("--inflight", type=int, default=10, help="frames in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
