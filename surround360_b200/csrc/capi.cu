@@ -336,7 +336,7 @@ int s360_sharpen(s360_ctx* c, uint8_t* bgr, int w, int h, double sharpening) {
   DeviceBuffer dRaw(px * 3), dS(px * 4), dF(px * 12), dLp(px * 8);
   S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.p, bgr, px * 3, cudaMemcpyHostToDevice, st));
   launchUnpackBGRA(st, dRaw.as<uint8_t>(), 3, w, h, dS.as<uchar4>());
-  launchSharpen(st, dS.as<uchar4>(), w, h, (float)(1.0f + sharpening), dF.as<float>(), dLp.as<uchar4>());
+  launchSharpen(st, dS.as<uchar4>(), w, h, 1, (float)(1.0f + sharpening), dF.as<float>(), dLp.as<uchar4>());
   launchPackBGR(st, dS.as<uchar4>(), w, h, w, dRaw.as<uint8_t>());
   S360_CUDA_CHECK(cudaMemcpyAsync(bgr, dRaw.p, px * 3, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -137,8 +137,10 @@ void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const
 // Each recurrence is sequential by definition (one thread per line, 3 channels of ILP);
 // parallelism comes from the 4096..8400 independent lines per eye.
 // ------------------------------------------------------------------------------------
-__global__ void k_transpose4(const uchar4* __restrict__ src, int w, int h, uchar4* __restrict__ dst) {
+__global__ void k_transpose4(const uchar4* __restrict__ srcAll, int w, int h, uchar4* __restrict__ dstAll) {
   __shared__ uchar4 tile[32][33];
+  const uchar4* __restrict__ src = srcAll + (size_t)w * h * blockIdx.z;
+  uchar4* __restrict__ dst = dstAll + (size_t)w * h * blockIdx.z;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int x = bx + threadIdx.x, y = by + r;
@@ -156,31 +158,55 @@ __device__ __forceinline__ int iirBoundary(int i, int n) {
   return i < 0 ? -i : i >= n ? 2 * n - i - 2 : i;
 }
 __device__ __forceinline__ float clamp255(float v) { return v < 0.0f ? 0.0f : v > 255.0f ? 255.0f : v; }
-// in/out: w columns, n rows (line length n along y). buf: 3 planes of [n][w] floats.
+// in/out: w columns, n rows (line length n along y), `eyes` images back to back (blockIdx.y).
+// buf: per eye 3 planes of [n][w] floats. One thread per line; the recurrence is sequential by
+// definition, so the loads of the next kIirBatch rows are issued together before the dependent
+// multiply-adds consume them (otherwise every step would expose a full memory round trip).
+constexpr int kIirBatch = 8;
 template <bool WRAP>
 __global__ void __launch_bounds__(128)
-k_iir_columns(const uchar4* __restrict__ in, int w, int n, float alpha, float* __restrict__ buf, uchar4* __restrict__ out) {
+k_iir_columns(const uchar4* __restrict__ inAll, int w, int n, float alpha, float* __restrict__ bufAll, uchar4* __restrict__ outAll) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
   const size_t plane = (size_t)w * n;
+  const uchar4* __restrict__ in = inAll + plane * blockIdx.y;
+  uchar4* __restrict__ out = outAll + plane * blockIdx.y;
+  float* __restrict__ buf = bufAll + 3 * plane * blockIdx.y;
   const float om = 1.0f - alpha;
-  uchar4 p0 = in[x];
+  const uchar4 p0 = in[x];
   float v0 = (float)p0.x, v1 = (float)p0.y, v2 = (float)p0.z;
-  for (int j = 1; j <= n; ++j) {  // causal
-    const uchar4 ip = in[(size_t)iirBoundary<WRAP>(j, n) * w + x];
-    v0 = (float)ip.x * om + v0 * alpha;
-    v1 = (float)ip.y * om + v1 * alpha;
-    v2 = (float)ip.z * om + v2 * alpha;
-    const size_t o = (size_t)iirBoundary<WRAP>(j - 1, n) * w + x;
-    buf[o] = v0; buf[plane + o] = v1; buf[2 * plane + o] = v2;
+  for (int j0 = 1; j0 <= n; j0 += kIirBatch) {  // causal: j = 1..n reads row boundary(j), writes row boundary(j-1)
+    uchar4 ip[kIirBatch];
+#pragma unroll
+    for (int u = 0; u < kIirBatch; ++u)
+      if (j0 + u <= n) ip[u] = in[(size_t)iirBoundary<WRAP>(j0 + u, n) * w + x];
+#pragma unroll
+    for (int u = 0; u < kIirBatch; ++u)
+      if (j0 + u <= n) {
+        v0 = (float)ip[u].x * om + v0 * alpha;
+        v1 = (float)ip[u].y * om + v1 * alpha;
+        v2 = (float)ip[u].z * om + v2 * alpha;
+        const size_t o = (size_t)iirBoundary<WRAP>(j0 + u - 1, n) * w + x;
+        buf[o] = v0; buf[plane + o] = v1; buf[2 * plane + o] = v2;
+      }
   }
-  for (int j = n - 2; j >= -1; --j) {  // anticausal
-    const size_t o = (size_t)iirBoundary<WRAP>(j, n) * w + x;
-    v0 = buf[o] * om + v0 * alpha;
-    v1 = buf[plane + o] * om + v1 * alpha;
-    v2 = buf[2 * plane + o] * om + v2 * alpha;
-    out[(size_t)(j + 1) * w + x] =
-        make_uchar4((unsigned char)truncU8(clamp255(v0)), (unsigned char)truncU8(clamp255(v1)), (unsigned char)truncU8(clamp255(v2)), 255);
+  for (int j0 = n - 2; j0 >= -1; j0 -= kIirBatch) {  // anticausal: j = n-2..-1 reads buffer row boundary(j), writes row j+1
+    float b0[kIirBatch], b1[kIirBatch], b2[kIirBatch];
+#pragma unroll
+    for (int u = 0; u < kIirBatch; ++u)
+      if (j0 - u >= -1) {
+        const size_t o = (size_t)iirBoundary<WRAP>(j0 - u, n) * w + x;
+        b0[u] = buf[o]; b1[u] = buf[plane + o]; b2[u] = buf[2 * plane + o];
+      }
+#pragma unroll
+    for (int u = 0; u < kIirBatch; ++u)
+      if (j0 - u >= -1) {
+        v0 = b0[u] * om + v0 * alpha;
+        v1 = b1[u] * om + v1 * alpha;
+        v2 = b2[u] * om + v2 * alpha;
+        out[(size_t)(j0 - u + 1) * w + x] =
+            make_uchar4((unsigned char)truncU8(clamp255(v0)), (unsigned char)truncU8(clamp255(v1)), (unsigned char)truncU8(clamp255(v2)), 255);
+      }
   }
 }
 __global__ void k_unsharp(uchar4* __restrict__ img, const uchar4* __restrict__ lp, size_t n, float amount) {
@@ -197,17 +223,18 @@ __global__ void k_unsharp(uchar4* __restrict__ img, const uchar4* __restrict__ l
   p.x = one(p.x, l.x); p.y = one(p.y, l.y); p.z = one(p.z, l.z);
   img[i] = p;
 }
-void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, float amount, float* scratchF, uchar4* scratchLp) {
-  // scratchLp holds two w*h uchar4 planes
+// img: `eyes` images of w x h back to back, sharpened in place.
+// scratchF: eyes * 3 * w * h floats; scratchLp: 2 * eyes * w * h uchar4.
+void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, int eyes, float amount, float* scratchF, uchar4* scratchLp) {
   uchar4* tA = scratchLp;
-  uchar4* tB = scratchLp + (size_t)w * h;
+  uchar4* tB = scratchLp + (size_t)eyes * w * h;
   const float alpha = powf(0.25f, 1.0f / 4.0f);
   dim3 tb(32, 8);
-  k_transpose4<<<dim3(iDivUp(w, 32), iDivUp(h, 32)), tb, 0, st>>>(img, w, h, tA);                  // tA: h wide, w tall
-  k_iir_columns<true><<<iDivUp(h, 128), 128, 0, st>>>(tA, h, w, alpha, scratchF, tB);               // horizontal pass (wrap)
-  k_transpose4<<<dim3(iDivUp(h, 32), iDivUp(w, 32)), tb, 0, st>>>(tB, h, w, tA);                  // tA: w wide, h tall
-  k_iir_columns<false><<<iDivUp(w, 128), 128, 0, st>>>(tA, w, h, alpha, scratchF, tB);              // vertical pass (reflect)
-  const size_t n = (size_t)w * h;
+  k_transpose4<<<dim3(iDivUp(w, 32), iDivUp(h, 32), eyes), tb, 0, st>>>(img, w, h, tA);                 // tA: h wide, w tall
+  k_iir_columns<true><<<dim3(iDivUp(h, 128), eyes), 128, 0, st>>>(tA, h, w, alpha, scratchF, tB);       // horizontal pass (wrap)
+  k_transpose4<<<dim3(iDivUp(h, 32), iDivUp(w, 32), eyes), tb, 0, st>>>(tB, h, w, tA);                 // tA: w wide, h tall
+  k_iir_columns<false><<<dim3(iDivUp(w, 128), eyes), 128, 0, st>>>(tA, w, h, alpha, scratchF, tB);      // vertical pass (reflect)
+  const size_t n = (size_t)eyes * w * h;
   k_unsharp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, tB, n, amount);
   g_launchCount += 5;
 }

@@ -89,9 +89,9 @@ void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w
 void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const uchar4* topLayer, const uchar4* botLayer,
                         int poleRows, uchar4* out, const RemapTables& rt);
 
-// sharpenThread: iirLowPass (wrap / reflect) + sharpenWithIirLowPass, in place on BGRA storage.
-// scratch: w*h*3 floats + w*h uchar4
-void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, float amount, float* scratchF, uchar4* scratchLp);
+// sharpenThread: iirLowPass (wrap / reflect) + sharpenWithIirLowPass, in place on BGRA storage, for
+// `eyes` images stored back to back. scratch: eyes*w*h*3 floats + 2*eyes*w*h uchar4
+void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, int eyes, float amount, float* scratchF, uchar4* scratchLp);
 
 // ---------------- flow_kernels.cu ----------------
 struct FlowParams {  // OpticalFlowFactory.h:25-61

@@ -196,7 +196,8 @@ struct FramePlan {
   DeviceBuffer featherScratch;
   DeviceBuffer poleFlow;            // [nPole][poleH][extW] float2
   DeviceBuffer poleWarped;          // [nPole][poleH][eqrW]
-  DeviceBuffer eye[2];              // eqrW x eqrH uchar4
+  DeviceBuffer eyes;                // 2 x (eqrW x eqrH) uchar4, left then right
+  uchar4* eye(int e, size_t eqPx) const { return eyes.as<uchar4>() + (size_t)e * eqPx; }
   DeviceBuffer eyePre[2];           // copy before sharpening (keepIntermediates)
   DeviceBuffer sharpF, sharpLp;
   DeviceBuffer outEq, outCube;      // device outputs for the host variant
@@ -264,8 +265,8 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
     F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP);
     (void)c->blurKernelFor(P.std_alpha_feather_size);  // allocate now: nothing may allocate while a frame is captured
   }
-  for (int e = 0; e < 2; ++e) F.eye[e].alloc(eqPx * 4);
-  if (P.sharpening > 0.0f) { F.sharpF.alloc(eqPx * 3 * 4); F.sharpLp.alloc(eqPx * 4 * 2); }
+  F.eyes.alloc(eqPx * 4 * 2);   // both eyes back to back so one launch sharpens them together
+  if (P.sharpening > 0.0f) { F.sharpF.alloc(eqPx * 3 * 4 * 2); F.sharpLp.alloc(eqPx * 4 * 2 * 2); }
   for (auto& e : F.ev) S360_CUDA_CHECK(cudaEventCreate(&e));
   F.valid = true;
   c->plan = std::move(plan);
@@ -388,19 +389,18 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
     }
   }
   // flatten (or plain copy when no poles): eye = BGRA panorama with the pole layers merged
-  launchFlattenPoles(st, F.panoL.as<uchar4>(), eqW, eqH, topLayer[0], botLayer[0], g.poleH, F.eye[0].as<uchar4>(), c->rt);
-  launchFlattenPoles(st, F.panoR.as<uchar4>(), eqW, eqH, topLayer[1], botLayer[1], g.poleH, F.eye[1].as<uchar4>(), c->rt);
+  launchFlattenPoles(st, F.panoL.as<uchar4>(), eqW, eqH, topLayer[0], botLayer[0], g.poleH, F.eye(0, (size_t)eqW * eqH), c->rt);
+  launchFlattenPoles(st, F.panoR.as<uchar4>(), eqW, eqH, topLayer[1], botLayer[1], g.poleH, F.eye(1, (size_t)eqW * eqH), c->rt);
   stageEvent(4);
 
   // ---- sharpen (TRSP:901-913) ----
   if (c->keepIntermediates)
     for (int e = 0; e < 2; ++e) {
       F.eyePre[e].ensure((size_t)eqW * eqH * 4);
-      S360_CUDA_CHECK(cudaMemcpyAsync(F.eyePre[e].p, F.eye[e].p, (size_t)eqW * eqH * 4, cudaMemcpyDeviceToDevice, st));
+      S360_CUDA_CHECK(cudaMemcpyAsync(F.eyePre[e].p, F.eye(e, (size_t)eqW * eqH), (size_t)eqW * eqH * 4, cudaMemcpyDeviceToDevice, st));
     }
   if (P.sharpening > 0.0f)
-    for (int e = 0; e < 2; ++e)
-      launchSharpen(st, F.eye[e].as<uchar4>(), eqW, eqH, (float)(1.0f + P.sharpening), F.sharpF.as<float>(), F.sharpLp.as<uchar4>());
+    launchSharpen(st, F.eyes.as<uchar4>(), eqW, eqH, 2, (float)(1.0f + P.sharpening), F.sharpF.as<float>(), F.sharpLp.as<uchar4>());
   stageEvent(5);
 
   // ---- cubemap + final equirect (TRSP:915-961) ----
@@ -408,12 +408,12 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
   frameOutputSize(c, P, &oW, &oH, &cW, &cH);
   if (cW > 0 && cubemapDev)
     for (int e = 0; e < 2; ++e)
-      launchCubemap(st, F.eye[e].as<uchar4>(), eqW, eqH, P.cubemap_width, P.cubemap_height, P.cubemap_photo,
+      launchCubemap(st, F.eye(e, (size_t)eqW * eqH), eqW, eqH, P.cubemap_width, P.cubemap_height, P.cubemap_photo,
                     cubemapDev + (size_t)e * cW * (cH / 2) * 3, c->rt);
   for (int e = 0; e < 2; ++e) {
     uint8_t* dst = equirectDev + (size_t)e * oW * (oH / 2) * 3;
-    if (oW != eqW || oH / 2 != eqH) launchResizeCubic8(st, F.eye[e].as<uchar4>(), eqW, eqH, eqW, 3, nullptr, oW, oH / 2, oW, dst);
-    else launchPackBGR(st, F.eye[e].as<uchar4>(), eqW, eqH, eqW, dst);
+    if (oW != eqW || oH / 2 != eqH) launchResizeCubic8(st, F.eye(e, (size_t)eqW * eqH), eqW, eqH, eqW, 3, nullptr, oW, oH / 2, oW, dst);
+    else launchPackBGR(st, F.eye(e, (size_t)eqW * eqH), eqW, eqH, eqW, dst);
   }
   stageEvent(6);
 }
