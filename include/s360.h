@@ -64,6 +64,9 @@ typedef struct {
   int cubemap_photo;              /* cubemap_format == "photo" (default "video") */
   char side_flow_alg[32];         /* "pixflow_low" */
   char polar_flow_alg[32];        /* "pixflow_low" */
+  int enable_pole_removal;        /* 0; needs s360_set_pole_masks */
+  int reserved0;
+  char poleremoval_flow_alg[32];  /* "pixflow_low" */
 } s360_params;
 
 const char* s360_last_error(void);
@@ -108,6 +111,11 @@ int s360_camera_pixel(s360_ctx* ctx, int cam, const double xyz[3], double out_xy
  * rank 0 serialises, every rank deserialises. */
 int s360_rig_serialize(s360_ctx* ctx, void* buf, size_t cap, size_t* used);
 int s360_rig_deserialize(s360_ctx* ctx, const void* buf, size_t len);
+
+/* Pole masks of --bottom_pole_masks_dir (<dir>/<bottomCamId>.png and <dir>/<bottomCam2Id>.png loaded as
+ * BGR8, TRSP:569-597, PoleRemoval.cpp:58-67): pixels equal to pure red (0,0,255) are cut out of the alpha
+ * channel. Host pointers, both w x h (the camera image size); copied to the device. */
+int s360_set_pole_masks(s360_ctx* ctx, const uint8_t* mask_bottom_bgr, const uint8_t* mask_bottom2_bgr, int w, int h);
 
 /* ---- geometry derived from rig + params (TRSP:155-162,309-316,340-348) ---- */
 typedef struct {
@@ -171,7 +179,7 @@ int s360_render_frame_dev(s360_ctx* ctx, const s360_params* p, const uint8_t* co
 
 /* Intermediates of the last s360_render_frame* call on this context, copied to host for
  * stage-wise parity tests. name: "projection"(idx=side cam) "flowLtoR"/"flowRtoL"(idx=pair)
- * "panoL" "panoR" "topSpherical" "bottomSpherical" "poleFlow"(0..3) "poleWarped"(0..3)
+ * "panoL" "panoR" "topSpherical" "bottomSpherical" "bottomMerged" "poleFlow"(0..3) "poleWarped"(0..3)
  * "eyeL" "eyeR". Query size with out == NULL. is_float: 0 = uint8, 1 = float32. */
 int s360_frame_intermediate(s360_ctx* ctx, const char* name, int idx, void* out, int* w, int* h, int* channels,
                             int* is_float);

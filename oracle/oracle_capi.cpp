@@ -47,6 +47,7 @@ struct ORenderParams {  // mirrors orc::RenderParams (POD for ctypes)
   int eqr_width, eqr_height, final_eqr_width, final_eqr_height, cubemap_width, cubemap_height;
   int want_cubemap, cubemap_photo, threads, keep_intermediates;
   int side_search20, polar_search20;
+  int enable_pole_removal;
 };
 static RenderParams toParams(const ORenderParams* p) {
   RenderParams P;
@@ -59,6 +60,7 @@ static RenderParams toParams(const ORenderParams* p) {
   P.threads = p->threads; P.keep_intermediates = p->keep_intermediates;
   P.side_flow_alg = p->side_search20 ? "pixflow_search_20" : "pixflow_low";
   P.polar_flow_alg = p->polar_search20 ? "pixflow_search_20" : "pixflow_low";
+  P.enable_pole_removal = p->enable_pole_removal != 0;
   return P;
 }
 
@@ -107,6 +109,7 @@ double o_camera_distort(void* rp, int cam, double r) { return ((Rig*)rp)->rig[ca
 double o_camera_undistort(void* rp, int cam, double d) { return ((Rig*)rp)->rig[cam].undistort(d); }
 float o_approximate_fov(void* rp, int vertical) { return approximateFov(((Rig*)rp)->side, vertical != 0); }
 float o_ring_radius(void* rp) { return ((Rig*)rp)->ringRadius(); }
+float o_usable_radius(void* rp, int cam) { return Camera::approximateUsablePixelsRadius(((Rig*)rp)->rig[cam]); }
 
 // geometry: fills ints camW camH overlapW numNovel, floats hRad vRad fovHRad slabDisp shiftPx
 void o_side_geometry(void* rp, const ORenderParams* p, int* oi, float* of) {
@@ -197,12 +200,14 @@ void o_pole_to_side(void* rp, const ORenderParams* p, const uint8_t* side, int s
 }
 
 // full frame. images: array of pointers to BGR frames (w*h*3) in rig order.
-void* o_render_frame(void* rp, const uint8_t** images, int iw, int ih, const ORenderParams* p) {
+void* o_render_frame(void* rp, const uint8_t** images, int iw, int ih, const ORenderParams* p, const uint8_t* mask1, const uint8_t* mask2) {
   try {
     Rig* r = (Rig*)rp;
     std::vector<Img8> im;
     for (size_t i = 0; i < r->rig.size(); ++i) im.push_back(wrap8(images[i], iw, ih, 3));
-    return new FrameResult(renderFrame(*r, im, toParams(p)));
+    Img8 m1, m2;
+    if (mask1 && mask2) { m1 = wrap8(mask1, iw, ih, 3); m2 = wrap8(mask2, iw, ih, 3); }
+    return new FrameResult(renderFrame(*r, im, toParams(p), mask1 ? &m1 : nullptr, mask2 ? &m2 : nullptr));
   } catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
 void o_result_free(void* f) { delete (FrameResult*)f; }
@@ -214,7 +219,7 @@ int o_result_get(void* fp, const char* name, int idx, const void** ptr, int* w, 
   else if (n == "projection") a = &f->projections.at(idx);
   else if (n == "flowLtoR") b = &f->flowLtoR.at(idx); else if (n == "flowRtoL") b = &f->flowRtoL.at(idx);
   else if (n == "panoL") a = &f->panoL; else if (n == "panoR") a = &f->panoR;
-  else if (n == "topSpherical") a = &f->topSpherical; else if (n == "bottomSpherical") a = &f->bottomSpherical;
+  else if (n == "bottomMerged") a = &f->bottomMerged; else if (n == "topSpherical") a = &f->topSpherical; else if (n == "bottomSpherical") a = &f->bottomSpherical;
   else if (n == "poleFlow") b = &f->poleFlow[idx]; else if (n == "poleWarped") a = &f->poleWarped[idx];
   else if (n == "eyeL") a = &f->eyeL; else if (n == "eyeR") a = &f->eyeR;
   else return 1;

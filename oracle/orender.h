@@ -25,7 +25,8 @@ struct RenderParams {  // gflags of TRSP:44-70 that affect pixels
   int side_alpha_feather_size = 100;
   int std_alpha_feather_size = 31;
   double sharpening = 0.0;
-  bool enable_top = false, enable_bottom = false;
+  bool enable_top = false, enable_bottom = false, enable_pole_removal = false;
+  std::string poleremoval_flow_alg = "pixflow_low";
   std::string side_flow_alg = "pixflow_low", polar_flow_alg = "pixflow_low";
   double zero_parallax_dist = 10000.0;
   int eqr_width = 256, eqr_height = 128;
@@ -395,7 +396,7 @@ struct FrameResult {
   std::vector<Img8> projections;
   std::vector<ImgF> flowLtoR, flowRtoL;
   Img8 panoL, panoR;  // after offsetHorizontalWrap, before padding
-  Img8 topSpherical, bottomSpherical;
+  Img8 topSpherical, bottomSpherical, bottomMerged;
   ImgF poleFlow[4];   // top_left, top_right, bottom_left, bottom_right
   Img8 poleWarped[4];
   Img8 eyeL, eyeR;    // BGR before sharpening
@@ -472,18 +473,77 @@ static inline void poleToSideFlow(const Rig& rig, const RenderParams& P, const I
   warpedOut = padRows(warped, 0, sideSpherical.h - rows);
 }
 
+// ---------------- CvUtil.cpp:201-222 ----------------
+static inline void circleAlphaCut(Img8& bgra, float radius) {
+  for (int y = 0; y < bgra.h; ++y)
+    for (int x = 0; x < bgra.w; ++x) {
+      const float dx = float(x) - float(bgra.w) / 2.0f, dy = float(y) - float(bgra.h) / 2.0f;
+      const float r = sqrtf(dx * dx + dy * dy);
+      const float alpha = r < radius ? 1.0f : 0.0f;
+      bgra.p(y, x)[3] = (unsigned char)(alpha * 255.0f);
+    }
+}
+static inline void cutRedMaskOutOfAlphaChannel(Img8& bgra, const Img8& maskBGR) {
+  for (int y = 0; y < maskBGR.h; ++y)
+    for (int x = 0; x < maskBGR.w; ++x) {
+      const uint8_t* m = maskBGR.p(y, x);
+      if (m[0] == 0 && m[1] == 0 && m[2] == 255) bgra.p(y, x)[3] = 0;
+    }
+}
+// ---------------- PoleRemoval.cpp:32-188 (prev_frame_data_dir NONE) ----------------
+static inline Img8 combineBottomImagesWithPoleRemoval(const Img8& bottomBGR, const Img8& bottom2BGR, const Img8& mask, const Img8& mask2,
+                                                      float radius, float radius2, bool flip180, const std::string& flowAlg,
+                                                      int featherSize, ImgF* flowOut = nullptr) {
+  Img8 b1 = bgr2bgra(bottomBGR), b2 = bgr2bgra(bottom2BGR);
+  circleAlphaCut(b1, radius);
+  circleAlphaCut(b2, radius2);
+  cutRedMaskOutOfAlphaChannel(b1, mask);
+  cutRedMaskOutOfAlphaChannel(b2, mask2);
+  b1 = featherAlphaChannel(b1, featherSize);
+  b2 = featherAlphaChannel(b2, featherSize);
+  if (flip180) b2 = flipBoth(b2);
+  ImgF flow;
+  PixFlow pf(flowParamsByName(flowAlg));
+  pf.computeOpticalFlow(b1, b2, ImgF(), Img8(), Img8(), flow, HINT_DOWN);
+  if (flowOut) *flowOut = flow;
+  ImgF warp(b1.w, b1.h, 2);
+  for (int y = 0; y < b1.h; ++y)
+    for (int x = 0; x < b1.w; ++x) {
+      warp.p(y, x)[0] = float(x) + flow.p(y, x)[0];
+      warp.p(y, x)[1] = float(y) + flow.p(y, x)[1];
+    }
+  Img8 warped2;
+  remapCubic8(b2, warp, warped2, B_CONSTANT);
+  for (int y = 0; y < b1.h; ++y)
+    for (int x = 0; x < b1.w; ++x) {
+      uint8_t* p1 = b1.p(y, x);
+      const uint8_t* p2 = warped2.p(y, x);
+      const float alpha = p1[3] / 255.0f, alpha2 = p2[3] / 255.0f;
+      if (alpha < 1.0f && alpha2 > 0.0f) {
+        const float a1 = alpha, a2 = 1.0f - alpha;
+        const float bb = a1 * float(p1[0]) + a2 * float(p2[0]), gg = a1 * float(p1[1]) + a2 * float(p2[1]),
+                    rr = a1 * float(p1[2]) + a2 * float(p2[2]);
+        p1[0] = (uint8_t)bb; p1[1] = (uint8_t)gg; p1[2] = (uint8_t)rr; p1[3] = 255;
+      }
+    }
+  circleAlphaCut(b1, radius);
+  return featherAlphaChannel(b1, featherSize);
+}
+
 // TRSP:647-685 (top) / 564-644 (bottom, no pole removal)
-static inline Img8 preparePoleSpherical(const Rig& rig, const RenderParams& P, const Img8& imgBGR, bool top) {
+static inline Img8 preparePoleSpherical(const Rig& rig, const RenderParams& P, const Img8& img, bool top) {
   const Camera& cam = rig.findByDirection(V3(0, 0, top ? 1 : -1));
   const int h = (int)(P.eqr_height * cam.getFov() / M_PI), w = P.eqr_width;
-  Img8 sph3;
+  // dst is created CV_8UC3, but cv::remap re-creates it with the source's type: a 4-channel source
+  // (pole removal) yields a 4-channel spherical image with the remapped alpha (TRSP:607-623)
+  Img8 sphAny;
   if (top)
-    sph3 = bicubicRemapToSpherical(w, h, 3, imgBGR, cam, (float)(2.0f * M_PI), 0.f, (float)(M_PI / 2.0f),
-                                   (float)(M_PI / 2.0f - cam.getFov()));
+    sphAny = bicubicRemapToSpherical(w, h, 3, img, cam, (float)(2.0f * M_PI), 0.f, (float)(M_PI / 2.0f),
+                                     (float)(M_PI / 2.0f - cam.getFov()));
   else
-    sph3 = bicubicRemapToSpherical(w, h, 3, imgBGR, cam, 0.f, (float)(2.0f * M_PI), (float)(-(M_PI / 2.0f)),
-                                   (float)(-(M_PI / 2.0f - cam.getFov())));
-  Img8 sph = bgr2bgra(sph3);
+    sphAny = bicubicRemapToSpherical(w, h, 3, img, cam, 0.f, (float)(2.0f * M_PI), (float)(-(M_PI / 2.0f)),
+                                     (float)(-(M_PI / 2.0f - cam.getFov())));
+  Img8 sph = sphAny.c == 4 ? sphAny : bgr2bgra(sphAny);
   const int yStart = h - 1 - P.std_alpha_feather_size;
   for (int y = std::max(yStart, 0); y < h; ++y) {
     const float alpha = 1.0f - float(y - yStart) / float(P.std_alpha_feather_size);
@@ -494,7 +554,8 @@ static inline Img8 preparePoleSpherical(const Rig& rig, const RenderParams& P, c
 }
 
 // images: rig.rig.size() BGR frames in rig order (index = position in the rig JSON)
-static inline FrameResult renderFrame(const Rig& rig, const std::vector<Img8>& images, const RenderParams& P) {
+static inline FrameResult renderFrame(const Rig& rig, const std::vector<Img8>& images, const RenderParams& P,
+                                      const Img8* poleMask = nullptr, const Img8* poleMask2 = nullptr) {
   FrameResult R;
   const double t0 = nowSec();
   const int numCams = (int)rig.side.size();
@@ -509,7 +570,21 @@ static inline FrameResult renderFrame(const Rig& rig, const std::vector<Img8>& i
   Img8 topSph, botSph;
   std::thread topThread, botThread;
   auto topJob = [&] { topSph = preparePoleSpherical(rig, P, imageOf(rig.findByDirection(V3(0, 0, 1)).id), true); };
-  auto botJob = [&] { botSph = preparePoleSpherical(rig, P, imageOf(rig.findByDirection(V3(0, 0, -1)).id), false); };
+  auto botJob = [&] {
+    const Camera& cam = rig.findByDirection(V3(0, 0, -1));
+    if (P.enable_pole_removal) {  // TRSP:569-597
+      if (!poleMask || !poleMask2) throw std::runtime_error("missing or bad pole mask");
+      const Camera& cam2 = rig.findLargestAxisDist();
+      const bool flip180 = cam.up().dot(cam2.up()) < 0;
+      Img8 merged = combineBottomImagesWithPoleRemoval(imageOf(cam.id), imageOf(cam2.id), *poleMask, *poleMask2,
+                                                       Camera::approximateUsablePixelsRadius(cam), Camera::approximateUsablePixelsRadius(cam2),
+                                                       flip180, P.poleremoval_flow_alg, P.std_alpha_feather_size);
+      if (P.keep_intermediates) R.bottomMerged = merged;
+      botSph = preparePoleSpherical(rig, P, merged, false);
+    } else {
+      botSph = preparePoleSpherical(rig, P, imageOf(cam.id), false);
+    }
+  };
   if (P.enable_bottom) { if (P.threads) botThread = std::thread(botJob); else botJob(); }
   if (P.enable_top) { if (P.threads) topThread = std::thread(topJob); else topJob(); }
 

@@ -29,7 +29,8 @@ class S360Params(C.Structure):
                 ("eqr_width", C.c_int), ("eqr_height", C.c_int), ("final_eqr_width", C.c_int),
                 ("final_eqr_height", C.c_int), ("cubemap_width", C.c_int), ("cubemap_height", C.c_int),
                 ("want_cubemap", C.c_int), ("cubemap_photo", C.c_int),
-                ("side_flow_alg", C.c_char * 32), ("polar_flow_alg", C.c_char * 32)]
+                ("side_flow_alg", C.c_char * 32), ("polar_flow_alg", C.c_char * 32),
+                ("enable_pole_removal", C.c_int), ("reserved0", C.c_int), ("poleremoval_flow_alg", C.c_char * 32)]
 
 
 class S360Geometry(C.Structure):
@@ -239,6 +240,10 @@ class Context:
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().s360_frame_output_size(self.h, C.byref(params), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return a.value, b.value, c.value, d.value
+
+    def set_pole_masks(self, mask_bottom_bgr, mask_bottom2_bgr):
+        m1, m2 = _c(mask_bottom_bgr, np.uint8), _c(mask_bottom2_bgr, np.uint8)
+        _check(lib().s360_set_pole_masks(self.h, _p(m1), _p(m2), m1.shape[1], m1.shape[0]))
 
     def keep_intermediates(self, on=True):
         _check(lib().s360_ctx_set_keep_intermediates(self.h, int(on)))

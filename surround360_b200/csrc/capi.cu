@@ -33,6 +33,7 @@ void s360_params_default(s360_params* p) {
   p->cubemap_width = 1536; p->cubemap_height = 1536;
   std::strcpy(p->side_flow_alg, "pixflow_low");
   std::strcpy(p->polar_flow_alg, "pixflow_low");
+  std::strcpy(p->poleremoval_flow_alg, "pixflow_low");
 }
 
 int s360_ctx_create(int device, s360_ctx** out) {
@@ -164,6 +165,17 @@ int s360_rig_deserialize(s360_ctx* c, const void* buf, size_t len) {
   c->rig = r;
   c->rigLoaded = true;
   resetPlan(c);
+  S360_API_END
+}
+int s360_set_pole_masks(s360_ctx* c, const uint8_t* m1, const uint8_t* m2, int w, int h) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(m1 && m2 && w > 0 && h > 0, "missing or bad pole mask");
+  const size_t bytes = (size_t)w * h * 3;
+  c->poleMasks.ensure(bytes * 2);
+  S360_CUDA_CHECK(cudaMemcpy(c->poleMasks.p, m1, bytes, cudaMemcpyHostToDevice));
+  S360_CUDA_CHECK(cudaMemcpy(c->poleMasks.as<uint8_t>() + bytes, m2, bytes, cudaMemcpyHostToDevice));
+  c->poleMaskW = w; c->poleMaskH = h;
   S360_API_END
 }
 int s360_geometry_query(s360_ctx* c, const s360_params* p, s360_geometry* out) {

@@ -98,7 +98,6 @@ int run(int argc, char** argv) {
   if (F.s("prev_frame_data_dir") != "NONE")
     throw VrCamException("prev_frame_data_dir != NONE: temporal regularisation is available per flow (s360_flow_compute) but the frame "
                          "pipeline of this build renders frames independently");
-  if (F.b("enable_pole_removal")) throw VrCamException("enable_pole_removal is not supported by this build (primary bottom camera only)");
 
   s360_ctx* ctx = nullptr;
   check(s360_ctx_create(F.i("device"), &ctx));
@@ -108,6 +107,8 @@ int run(int argc, char** argv) {
   P.interpupilary_dist = F.d("interpupilary_dist"); P.sharpening = F.d("sharpening"); P.zero_parallax_dist = F.d("zero_parallax_dist");
   P.side_alpha_feather_size = F.i("side_alpha_feather_size"); P.std_alpha_feather_size = F.i("std_alpha_feather_size");
   P.enable_top = F.b("enable_top"); P.enable_bottom = F.b("enable_bottom");
+  P.enable_pole_removal = F.b("enable_pole_removal");
+  std::strncpy(P.poleremoval_flow_alg, F.s("poleremoval_flow_alg").c_str(), sizeof(P.poleremoval_flow_alg) - 1);
   P.eqr_width = F.i("eqr_width"); P.eqr_height = F.i("eqr_height");
   P.final_eqr_width = F.i("final_eqr_width"); P.final_eqr_height = F.i("final_eqr_height");
   P.cubemap_width = F.i("cubemap_width"); P.cubemap_height = F.i("cubemap_height");
@@ -140,6 +141,18 @@ int run(int argc, char** argv) {
   }
   if (P.enable_top) load(s360_rig_special_camera(ctx, 0), "png");
   if (P.enable_bottom) load(s360_rig_special_camera(ctx, 1), "png");
+  if (P.enable_bottom && P.enable_pole_removal) {  // TRSP:569-597, PoleRemoval.cpp:52-67
+    requireArg(F, "bottom_pole_masks_dir");
+    const int cam2 = s360_rig_special_camera(ctx, 2);
+    load(cam2, "png");
+    const std::string md = F.s("bottom_pole_masks_dir");
+    const std::string p1 = md + "/" + s360_rig_camera_id(ctx, s360_rig_special_camera(ctx, 1)) + ".png", p2 = md + "/" + s360_rig_camera_id(ctx, cam2) + ".png";
+    pngio::Image m1, m2;
+    try { m1 = pngio::readColor(p1); m2 = pngio::readColor(p2); }
+    catch (const std::exception&) { throw VrCamException("missing or bad pole mask:" + p1 + "," + p2); }
+    if (m1.w != iw || m1.h != ih || m2.w != iw || m2.h != ih) throw VrCamException("missing or bad pole mask:" + p1 + "," + p2);
+    check(s360_set_pole_masks(ctx, m1.data.data(), m2.data.data(), iw, ih));
+  }
   if (verbose) std::cerr << "Time to load images from file: " << nowSec() - t0 << " sec\n";
 
   // ---- render ----

@@ -83,6 +83,65 @@ void launchExtendWrap(cudaStream_t st, const uchar4* src, int w, int rows, uchar
 }
 
 // ------------------------------------------------------------------------------------
+// pole removal (PoleRemoval.cpp:32-188; circleAlphaCut / cutRedMaskOutOfAlphaChannel CvUtil.cpp:201-222)
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned char circleAlpha(int x, int y, int w, int h, float radius) {
+  const float dx = float(x) - float(w) / 2.0f, dy = float(y) - float(h) / 2.0f;
+  const float r = sqrtf(dx * dx + dy * dy);
+  return r < radius ? 255 : 0;
+}
+__global__ void k_pr_prepare(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask, int w, int h, float radius, uchar4* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const size_t i = (size_t)y * w + x;
+  const uint8_t* p = src + i * 3;
+  const uint8_t* m = mask + i * 3;
+  unsigned char a = circleAlpha(x, y, w, h, radius);
+  if (m[0] == 0 && m[1] == 0 && m[2] == 255) a = 0;
+  dst[i] = make_uchar4(p[0], p[1], p[2], a);
+}
+void launchPoleRemovalPrepare(cudaStream_t st, const uint8_t* srcBGR, const uint8_t* maskBGR, int w, int h, float radius, uchar4* dst) {
+  dim3 b(32, 8);
+  k_pr_prepare<<<grid2d(w, h, b), b, 0, st>>>(srcBGR, maskBGR, w, h, radius, dst);
+  ++g_launchCount;
+}
+__global__ void k_flip_both(const uchar4* __restrict__ src, int w, int h, uchar4* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  dst[(size_t)y * w + x] = __ldg(src + (size_t)(h - 1 - y) * w + (w - 1 - x));
+}
+void launchFlipBoth(cudaStream_t st, const uchar4* src, int w, int h, uchar4* dst) {
+  dim3 b(32, 8);
+  k_flip_both<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, dst);
+  ++g_launchCount;
+}
+__global__ void __launch_bounds__(256)
+k_pr_merge(const uchar4* __restrict__ img1, const uchar4* __restrict__ img2, const float2* __restrict__ flow, int w, int h, float radius,
+           uchar4* __restrict__ dst, const short* __restrict__ tabI) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const size_t i = (size_t)y * w + x;
+  const float2 fl = __ldg(flow + i);
+  const uchar4 p2 = remapCubicBGRA<BORDER_CONST>(img2, w, h, w, float(x) + fl.x, float(y) + fl.y, tabI);
+  uchar4 p1 = __ldg(img1 + i);
+  const float alpha = (float)p1.w / 255.0f, alpha2 = (float)p2.w / 255.0f;
+  if (alpha < 1.0f && alpha2 > 0.0f) {
+    const float a1 = alpha, a2 = 1.0f - alpha;
+    p1.x = (unsigned char)truncU8(a1 * float(p1.x) + a2 * float(p2.x));
+    p1.y = (unsigned char)truncU8(a1 * float(p1.y) + a2 * float(p2.y));
+    p1.z = (unsigned char)truncU8(a1 * float(p1.z) + a2 * float(p2.z));
+  }
+  p1.w = circleAlpha(x, y, w, h, radius);   // circleAlphaCut overwrites the alpha of every pixel (PoleRemoval.cpp:181)
+  dst[i] = p1;
+}
+void launchPoleRemovalMerge(cudaStream_t st, const uchar4* img1, const uchar4* img2, const float2* flow, int w, int h, float radius,
+                            uchar4* dst, const RemapTables& rt) {
+  dim3 b(32, 8);
+  k_pr_merge<<<grid2d(w, h, b), b, 0, st>>>(img1, img2, flow, w, h, radius, dst, rt.wi);
+  ++g_launchCount;
+}
+
+// ------------------------------------------------------------------------------------
 // flattenLayersDeghostPreferBase (CvUtil.cpp:224-260)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ uchar4 flattenPixel(uchar4 base, uchar4 top, const RemapTables& rt) {

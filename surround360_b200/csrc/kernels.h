@@ -25,6 +25,7 @@ struct SphericalTables {  // per-destination-column / per-row trig, made on the 
 };
 // bicubicRemapToSpherical. poleMode 0: keep remapped alpha (side cameras). poleMode 1:
 // alpha = 255 then the std_alpha_feather ramp of TRSP:629-637 / 671-678 from row featherStart.
+// poleMode 2 (bottom image with pole removal): remapped alpha, min() with the ramp (TRSP:629-637).
 void launchProjectSpherical(cudaStream_t st, const uchar4* src, int sw, int sh, const DevCamera& cam,
                             const SphericalTables& tb, uchar4* dst, int dw, int dh, int dstPitch, int poleMode,
                             int featherStart, int featherSize, const RemapTables& rt);
@@ -92,6 +93,14 @@ void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const
 // sharpenThread: iirLowPass (wrap / reflect) + sharpenWithIirLowPass, in place on BGRA storage, for
 // `eyes` images stored back to back. scratch: eyes*w*h*3 floats + 2*eyes*w*h uchar4
 void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, int eyes, float amount, float* scratchF, uchar4* scratchLp);
+
+// pole removal (PoleRemoval.cpp:32-188). prepare: BGR + red mask -> BGRA with the usable-radius circle and the
+// mask cut out of alpha (CvUtil.cpp:201-222). merge: warp image2 by the flow (cubic), alpha-weighted
+// combination, new circle alpha (PoleRemoval.cpp:128-181).
+void launchPoleRemovalPrepare(cudaStream_t st, const uint8_t* srcBGR, const uint8_t* maskBGR, int w, int h, float radius, uchar4* dst);
+void launchFlipBoth(cudaStream_t st, const uchar4* src, int w, int h, uchar4* dst);
+void launchPoleRemovalMerge(cudaStream_t st, const uchar4* img1, const uchar4* img2, const float2* flow, int w, int h, float radius,
+                            uchar4* dst, const RemapTables& rt);
 
 // ---------------- flow_kernels.cu ----------------
 struct FlowParams {  // OpticalFlowFactory.h:25-61

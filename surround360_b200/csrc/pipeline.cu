@@ -192,6 +192,9 @@ struct FramePlan {
   DeviceBuffer flowSide;   // [2][numCams][camH][overlapW] float2: LtoR then RtoL
   DeviceBuffer panoL, panoR;        // eqrW x eqrH uchar4 (pad rows stay zero)
   DeviceBuffer topSph, botSph;      // eqrW x poleH
+  DeviceBuffer prA, prB, prC, prFlow, prScratch;   // pole removal work images (imgW x imgH)
+  std::unique_ptr<FlowBatch> prFlowBatch;
+  bool poleRemoval = false;
   DeviceBuffer extSide, extFish;    // [nPole][poleH][extW]
   DeviceBuffer featherScratch;
   DeviceBuffer poleFlow;            // [nPole][poleH][extW] float2
@@ -264,6 +267,16 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
     F.poleWarped.alloc(polePx * 4 * F.nPole);
     F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP);
     (void)c->blurKernelFor(P.std_alpha_feather_size);  // allocate now: nothing may allocate while a frame is captured
+    F.poleRemoval = F.bottom && P.enable_pole_removal != 0;
+    if (F.poleRemoval) {
+      FlowParams prFP;
+      if (!flowParamsByName(P.poleremoval_flow_alg, &prFP)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + P.poleremoval_flow_alg);
+      if (!c->poleMasks.p || c->poleMaskW != imgW || c->poleMaskH != imgH) throw std::runtime_error("missing or bad pole mask: call s360_set_pole_masks with masks of the camera image size");
+      const size_t ipx = (size_t)imgW * imgH;
+      F.prA.alloc(ipx * 4); F.prB.alloc(ipx * 4); F.prC.alloc(ipx * 4); F.prFlow.alloc(ipx * 8);
+      F.prScratch.alloc(featherScratchBytes(imgW, imgH));
+      F.prFlowBatch = std::make_unique<FlowBatch>(1, imgW, imgH, prFP);
+    }
   }
   F.eyes.alloc(eqPx * 4 * 2);   // both eyes back to back so one launch sharpens them together
   if (P.sharpening > 0.0f) { F.sharpF.alloc(eqPx * 3 * 4 * 2); F.sharpLp.alloc(eqPx * 4 * 2 * 2); }
@@ -315,9 +328,34 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
   }
   if (F.bottom) {
     const int ci = rig.bottomCamera();
-    launchPrepSource(st, imagesDev[ci], 3, imgW, imgH, 0, F.srcBGRA.as<uchar4>());
-    launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, rig.cameras[ci].toDevice(), F.botTables.t, F.botSph.as<uchar4>(), eqW,
-                           g.poleH, eqW, 1, std::max(featherStart, 0), P.std_alpha_feather_size, c->rt);
+    if (F.poleRemoval) {  // TRSP:569-597, PoleRemoval.cpp:32-188
+      const int ci2 = rig.findLargestDistCamAxisToRigCenter();
+      const Camera &cam = rig.cameras[ci], &cam2 = rig.cameras[ci2];
+      const bool flip180 = dot(cam.up(), cam2.up()) < 0;
+      const float r1 = cam.approximateUsablePixelsRadius(), r2 = cam2.approximateUsablePixelsRadius();
+      const int* fk = c->blurKernelFor(P.std_alpha_feather_size);
+      const uint8_t* m1 = c->poleMasks.as<uint8_t>();
+      const uint8_t* m2 = m1 + (size_t)imgW * imgH * 3;
+      uchar4 *A = F.prA.as<uchar4>(), *B = F.prB.as<uchar4>(), *C = F.prC.as<uchar4>();
+      launchPoleRemovalPrepare(st, imagesDev[ci], m1, imgW, imgH, r1, C);
+      launchFeatherAlpha(st, C, imgW, imgH, P.std_alpha_feather_size, fk, A, F.prScratch.as<uint8_t>());        // A = bottomImage
+      launchPoleRemovalPrepare(st, imagesDev[ci2], m2, imgW, imgH, r2, C);
+      launchFeatherAlpha(st, C, imgW, imgH, P.std_alpha_feather_size, fk, B, F.prScratch.as<uint8_t>());        // B = bottomImage2
+      if (flip180) { launchFlipBoth(st, B, imgW, imgH, C); std::swap(B, C); }
+      FlowImagePtrs ip{};
+      FlowPrevPtrs pv{};
+      ip.i0[0] = A; ip.i1[0] = B; ip.pitch0[0] = ip.pitch1[0] = imgW; ip.hint[0] = S360_HINT_DOWN;
+      F.prFlowBatch->run(st, ip, pv, F.prFlow.as<float2>());
+      launchPoleRemovalMerge(st, A, B, F.prFlow.as<float2>(), imgW, imgH, r1, C, c->rt);
+      launchFeatherAlpha(st, C, imgW, imgH, P.std_alpha_feather_size, fk, F.srcBGRA.as<uchar4>(), F.prScratch.as<uint8_t>());
+      if (c->keepIntermediates) S360_CUDA_CHECK(cudaMemcpyAsync(A, F.srcBGRA.p, (size_t)imgW * imgH * 4, cudaMemcpyDeviceToDevice, st));
+      launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, cam.toDevice(), F.botTables.t, F.botSph.as<uchar4>(), eqW,
+                             g.poleH, eqW, 2, std::max(featherStart, 0), P.std_alpha_feather_size, c->rt);
+    } else {
+      launchPrepSource(st, imagesDev[ci], 3, imgW, imgH, 0, F.srcBGRA.as<uchar4>());
+      launchProjectSpherical(st, F.srcBGRA.as<uchar4>(), imgW, imgH, rig.cameras[ci].toDevice(), F.botTables.t, F.botSph.as<uchar4>(), eqW,
+                             g.poleH, eqW, 1, std::max(featherStart, 0), P.std_alpha_feather_size, c->rt);
+    }
   }
   stageEvent(1);
 
@@ -533,6 +571,10 @@ int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w,
     if (!F.nPole) throw std::runtime_error("poles are not enabled");
     *w = eqW; *h = g.poleH; *ch = 4; *isFloat = 0;
     copy2d((n == "topSpherical" ? F.topSph : F.botSph).p, (size_t)eqW * 4, g.poleH, (size_t)eqW * 4);
+  } else if (n == "bottomMerged") {
+    if (!F.poleRemoval) throw std::runtime_error("pole removal is not enabled");
+    *w = F.imgW; *h = F.imgH; *ch = 4; *isFloat = 0;
+    copy2d(F.prA.p, (size_t)F.imgW * 4, F.imgH, (size_t)F.imgW * 4);
   } else if (n == "poleFlow" || n == "poleWarped") {
     // reference order: top_left, top_right, bottom_left, bottom_right
     int k = idx;

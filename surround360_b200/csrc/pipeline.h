@@ -48,6 +48,8 @@ struct s360_ctx {
   s360::RemapTables rt{};
   std::map<int, std::unique_ptr<s360::DeviceBuffer>> blurKernels;  // erodeSize -> 8.8 fixed-point taps
   std::unique_ptr<s360::FramePlan> plan;
+  s360::DeviceBuffer poleMasks;         // two BGR8 masks (bottom, bottom2), s360_set_pole_masks
+  int poleMaskW = 0, poleMaskH = 0;
   bool keepIntermediates = false;
   bool profile = false;
   bool useGraphs = true;

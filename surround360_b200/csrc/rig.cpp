@@ -213,6 +213,22 @@ Vec3 Camera::rigDirection(double px, double py) const {
           rotation[2] * ux + rotation[5] * uy + rotation[8] * uz};
 }
 
+float Camera::approximateUsablePixelsRadius() const {
+  const double fov = getFov();
+  const double kStep = 2 * M_PI / 10.0;
+  double result = std::sqrt(resolution[0] * resolution[0] + resolution[1] * resolution[1]);
+  const Vec3 r = right(), u = up(), f = forward();
+  for (double a = 0; a < 2 * M_PI; a += kStep) {
+    const Vec3 ortho = r * std::cos(a) + u * std::sin(a);
+    const Vec3 direction = f * std::cos(fov) + ortho * std::sin(fov);
+    double px, py;
+    pixel(position + direction, px, py);
+    const double dx = px - resolution[0] / 2.0, dy = py - resolution[1] / 2.0;
+    result = std::min(result, std::sqrt(dx * dx + dy * dy));
+  }
+  return (float)result;
+}
+
 // ------------------------------------------------------------------------------------
 // Rig
 // ------------------------------------------------------------------------------------

@@ -42,6 +42,8 @@ struct Camera {
   void pixel(const Vec3& rig, double& px, double& py) const;  // Camera.h:133-140
   // Camera::rig(pixel): origin = position, returns the (unnormalised) direction
   Vec3 rigDirection(double px, double py) const;
+  // Camera::approximateUsablePixelsRadius (Camera.h:201-212)
+  float approximateUsablePixelsRadius() const;
 };
 
 struct Rig {

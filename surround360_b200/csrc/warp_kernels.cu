@@ -85,10 +85,11 @@ k_project_spherical(const uchar4* __restrict__ src, int sw, int sh, DevCamera ca
   const float mx = (float)(px - 0.5), my = (float)(py - 0.5);
   uchar4 v = remapCubicBGRA<BORDER_CONST>(src, sw, sh, sw, mx, my, tabI);
   if (poleMode) {
-    v.w = 255;
+    if (poleMode == 1) v.w = 255;
     if (y >= featherStart) {
       const float alpha = 1.0f - float(y - featherStart) / float(featherSize);
-      v.w = (unsigned char)truncU8(255.0f * alpha);
+      const unsigned char ramp = (unsigned char)truncU8(255.0f * alpha);
+      v.w = poleMode == 1 ? ramp : min(v.w, ramp);
     }
   }
   dst[(size_t)y * dpitch + x] = v;

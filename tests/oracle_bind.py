@@ -17,11 +17,12 @@ class ORenderParams(C.Structure):
                 ("eqr_width", C.c_int), ("eqr_height", C.c_int), ("final_eqr_width", C.c_int),
                 ("final_eqr_height", C.c_int), ("cubemap_width", C.c_int), ("cubemap_height", C.c_int),
                 ("want_cubemap", C.c_int), ("cubemap_photo", C.c_int), ("threads", C.c_int),
-                ("keep_intermediates", C.c_int), ("side_search20", C.c_int), ("polar_search20", C.c_int)]
+                ("keep_intermediates", C.c_int), ("side_search20", C.c_int), ("polar_search20", C.c_int),
+                ("enable_pole_removal", C.c_int)]
 
 
 def make_params(**kw):
-    p = ORenderParams(6.4, 0.0, 10000.0, 100, 31, 0, 0, 256, 128, 3480, 960, 1536, 1536, 0, 0, 1, 0, 0, 0)
+    p = ORenderParams(6.4, 0.0, 10000.0, 100, 31, 0, 0, 256, 128, 3480, 960, 1536, 1536, 0, 0, 1, 0, 0, 0, 0)
     for k, v in kw.items():
         if not hasattr(p, k):
             raise KeyError(k)
@@ -45,6 +46,7 @@ def lib():
         L.o_camera_undistort.restype = C.c_double
         L.o_approximate_fov.restype = C.c_float
         L.o_ring_radius.restype = C.c_float
+        L.o_usable_radius.restype = C.c_float
         _LIB = L
     return _LIB
 
@@ -124,10 +126,14 @@ class Rig:
                              P(warped), P(flow))
         return warped, flow
 
-    def render_frame(self, images, p):
+    def render_frame(self, images, p, pole_masks=None):
         ims = [_c(i, np.uint8) for i in images]
         arr = (C.c_void_p * len(ims))(*[i.ctypes.data for i in ims])
-        h = lib().o_render_frame(self.h, arr, ims[0].shape[1], ims[0].shape[0], C.byref(p))
+        m1 = m2 = None
+        if pole_masks is not None:
+            m1, m2 = _c(pole_masks[0], np.uint8), _c(pole_masks[1], np.uint8)
+        h = lib().o_render_frame(self.h, arr, ims[0].shape[1], ims[0].shape[0], C.byref(p), P(m1) if m1 is not None else None,
+                                 P(m2) if m2 is not None else None)
         if not h:
             raise RuntimeError(lib().o_last_error().decode())
         return FrameResult(C.c_void_p(h))

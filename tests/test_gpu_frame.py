@@ -154,3 +154,24 @@ def test_cli_is_a_drop_in(ctx, frames17, tmp_path, rig_path):
     # error behaviour: unknown flow algorithm -> VrCamException text, non-zero exit
     r = subprocess.run(cmd + ["--side_flow_alg", "nope"], capture_output=True, text=True)
     assert r.returncode != 0 and "unrecognized flow algorithm name: nope" in r.stderr
+
+
+def test_pole_removal(ctx, orig, frames17):
+    """--enable_pole_removal (PoleRemoval.cpp:32-188): red-mask cut, feather, flip180, flow, warp, merge, re-cut."""
+    m1 = np.zeros((2048, 2048, 3), np.uint8); m1[900:1300, 980:1080] = (0, 0, 255)
+    m2 = np.zeros((2048, 2048, 3), np.uint8); m2[700:1100, 1000:1100] = (0, 0, 255)
+    m2[10:20, 10:20] = (0, 1, 255)    # not pure red: must not be cut
+    kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1024, final_eqr_height=1024, enable_bottom=1, enable_pole_removal=1)
+    ctx.set_pole_masks(m1, m2)
+    ctx.keep_intermediates(True)
+    eq = ctx.renderStereoPanorama(api.default_params(**kw), frames17)
+    ref = orig.render_frame(frames17, ob.make_params(keep_intermediates=1, **kw), (m1, m2))
+    close(ctx.intermediate("bottomMerged"), ref.get("bottomMerged"), "bottomMerged")
+    close(ctx.intermediate("bottomSpherical"), ref.get("bottomSpherical"), "bottomSpherical (pole removal)")
+    close(eq, ref.get("equirect"), "equirect (pole removal)")
+    c2 = api.Context(0)
+    from conftest import RIG17
+    c2.load_rig(RIG17)
+    with pytest.raises(api.VrCamException, match="missing or bad pole mask"):
+        c2.renderStereoPanorama(api.default_params(**kw), frames17)
+    c2.close()
