@@ -93,6 +93,13 @@ int s360_profile_enable(s360_ctx* ctx, int on);
 /* Whole-frame CUDA-graph replay (default on). Profiling, keep_intermediates and the stage timers
  * need the plain launch path and switch it off implicitly for the frames they cover. */
 int s360_ctx_set_graphs(s360_ctx* ctx, int on);
+/* Video mode (--prev_frame_data_dir != NONE, scripts/batch_process_video.py:137,157-158): when on, every frame
+ * rendered on this context regularises its flows against the previous frame rendered on it (PixFlow.h:101-118,
+ * 147-153, 165-167); the previous flows / overlap images / extended fisheye images stay on the device instead of
+ * going through .bin and PNG files (TRSP:200-255, 413-452). The first frame after enabling or after
+ * s360_ctx_reset_temporal renders like NONE. */
+int s360_ctx_set_temporal(s360_ctx* ctx, int on);
+int s360_ctx_reset_temporal(s360_ctx* ctx);
 int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, double* level_pixels, double* steps);
 
 /* ---- rig (RIG_JSON.md format) ---- */

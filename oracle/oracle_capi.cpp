@@ -200,14 +200,16 @@ void o_pole_to_side(void* rp, const ORenderParams* p, const uint8_t* side, int s
 }
 
 // full frame. images: array of pointers to BGR frames (w*h*3) in rig order.
-void* o_render_frame(void* rp, const uint8_t** images, int iw, int ih, const ORenderParams* p, const uint8_t* mask1, const uint8_t* mask2) {
+void* o_state_new() { return new FrameState(); }
+void o_state_free(void* s) { delete (FrameState*)s; }
+void* o_render_frame(void* rp, const uint8_t** images, int iw, int ih, const ORenderParams* p, const uint8_t* mask1, const uint8_t* mask2, void* state) {
   try {
     Rig* r = (Rig*)rp;
     std::vector<Img8> im;
     for (size_t i = 0; i < r->rig.size(); ++i) im.push_back(wrap8(images[i], iw, ih, 3));
     Img8 m1, m2;
     if (mask1 && mask2) { m1 = wrap8(mask1, iw, ih, 3); m2 = wrap8(mask2, iw, ih, 3); }
-    return new FrameResult(renderFrame(*r, im, toParams(p), mask1 ? &m1 : nullptr, mask2 ? &m2 : nullptr));
+    return new FrameResult(renderFrame(*r, im, toParams(p), mask1 ? &m1 : nullptr, mask2 ? &m2 : nullptr, (FrameState*)state));
   } catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
 void o_result_free(void* f) { delete (FrameResult*)f; }

@@ -403,6 +403,17 @@ struct FrameResult {
   double tProject = 0, tFlow = 0, tNovel = 0, tPole = 0, tSharpen = 0, tTotal = 0;
 };
 
+// What the next frame's temporal regularisation reads back (flow .bin files and overlap / extended PNGs in the
+// reference: TRSP:200-255, 413-452; lossless, so keeping them in memory is equivalent)
+struct FrameState {
+  bool valid = false;
+  std::vector<Img8> ovL, ovR;
+  std::vector<ImgF> fLR, fRL;
+  Img8 extSide[4], extFish[4];
+  ImgF poleFlow[4];
+  bool poleValid[4] = {false, false, false, false};
+};
+
 static inline double nowSec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -415,7 +426,8 @@ static inline void runAll(std::vector<std::function<void()>>& jobs, bool threads
 
 // TRSP:388-561
 static inline void poleToSideFlow(const Rig& rig, const RenderParams& P, const Img8& sideSpherical,
-                                  const Img8& fisheyeSpherical, Img8& warpedOut, ImgF* flowOut) {
+                                  const Img8& fisheyeSpherical, Img8& warpedOut, ImgF* flowOut, FrameState* state = nullptr,
+                                  int slot = 0) {
   const int cols = fisheyeSpherical.w, rows = fisheyeSpherical.h;
   Img8 cropped = featherAlphaChannel(cropRows(sideSpherical, rows), P.std_alpha_feather_size);
   const float kExtendFrac = 1.2f;
@@ -428,7 +440,11 @@ static inline void poleToSideFlow(const Rig& rig, const RenderParams& P, const I
     }
   ImgF flow;
   PixFlow pf(flowParamsByName(P.polar_flow_alg));
-  pf.computeOpticalFlow(extSide, extFish, ImgF(), Img8(), Img8(), flow, HINT_DOWN);
+  if (state && state->valid && state->poleValid[slot])  // TRSP:418-447
+    pf.computeOpticalFlow(extSide, extFish, state->poleFlow[slot], state->extSide[slot], state->extFish[slot], flow, HINT_DOWN);
+  else
+    pf.computeOpticalFlow(extSide, extFish, ImgF(), Img8(), Img8(), flow, HINT_DOWN);
+  if (state) { state->extSide[slot] = extSide; state->extFish[slot] = extFish; state->poleFlow[slot] = flow; state->poleValid[slot] = true; }
   if (flowOut) *flowOut = flow;
 
   float poleCameraRadius = (float)rig.findByDirection(V3(0, 0, -1)).getFov();
@@ -555,7 +571,7 @@ static inline Img8 preparePoleSpherical(const Rig& rig, const RenderParams& P, c
 
 // images: rig.rig.size() BGR frames in rig order (index = position in the rig JSON)
 static inline FrameResult renderFrame(const Rig& rig, const std::vector<Img8>& images, const RenderParams& P,
-                                      const Img8* poleMask = nullptr, const Img8* poleMask2 = nullptr) {
+                                      const Img8* poleMask = nullptr, const Img8* poleMask2 = nullptr, FrameState* state = nullptr) {
   FrameResult R;
   const double t0 = nowSec();
   const int numCams = (int)rig.side.size();
@@ -615,8 +631,13 @@ static inline FrameResult renderFrame(const Rig& rig, const std::vector<Img8>& i
         ovL[i] = cropCols(proj[i], proj[i].w - g.overlapW, g.overlapW);
         ovR[i] = cropCols(proj[r], 0, g.overlapW);
         PixFlow pf(flowParamsByName(P.side_flow_alg));
-        pf.computeOpticalFlow(ovL[i], ovR[i], ImgF(), Img8(), Img8(), fLR[i], HINT_LEFT);
-        pf.computeOpticalFlow(ovR[i], ovL[i], ImgF(), Img8(), Img8(), fRL[i], HINT_RIGHT);
+        if (state && state->valid) {  // TRSP:210-244, NovelView.cpp:282-297
+          pf.computeOpticalFlow(ovL[i], ovR[i], state->fLR[i], state->ovL[i], state->ovR[i], fLR[i], HINT_LEFT);
+          pf.computeOpticalFlow(ovR[i], ovL[i], state->fRL[i], state->ovR[i], state->ovL[i], fRL[i], HINT_RIGHT);
+        } else {
+          pf.computeOpticalFlow(ovL[i], ovR[i], ImgF(), Img8(), Img8(), fLR[i], HINT_LEFT);
+          pf.computeOpticalFlow(ovR[i], ovL[i], ImgF(), Img8(), Img8(), fRL[i], HINT_RIGHT);
+        }
       });
     runAll(jobs, P.threads);
   }
@@ -671,17 +692,18 @@ static inline FrameResult renderFrame(const Rig& rig, const std::vector<Img8>& i
   std::vector<std::function<void()>> poleJobs;
   if (P.enable_top) {
     if (topThread.joinable()) topThread.join();
-    poleJobs.push_back([&] { poleToSideFlow(rig, P, sphL, topSph, topWL, P.keep_intermediates ? &R.poleFlow[0] : nullptr); });
-    poleJobs.push_back([&] { poleToSideFlow(rig, P, sphR, topSph, topWR, P.keep_intermediates ? &R.poleFlow[1] : nullptr); });
+    poleJobs.push_back([&] { poleToSideFlow(rig, P, sphL, topSph, topWL, P.keep_intermediates ? &R.poleFlow[0] : nullptr, state, 0); });
+    poleJobs.push_back([&] { poleToSideFlow(rig, P, sphR, topSph, topWR, P.keep_intermediates ? &R.poleFlow[1] : nullptr, state, 1); });
   }
   if (P.enable_bottom) {
     if (botThread.joinable()) botThread.join();
     flipL = flipBoth(sphL);
     flipR = flipBoth(sphR);
-    poleJobs.push_back([&] { poleToSideFlow(rig, P, flipL, botSph, botWL, P.keep_intermediates ? &R.poleFlow[2] : nullptr); });
-    poleJobs.push_back([&] { poleToSideFlow(rig, P, flipR, botSph, botWR, P.keep_intermediates ? &R.poleFlow[3] : nullptr); });
+    poleJobs.push_back([&] { poleToSideFlow(rig, P, flipL, botSph, botWL, P.keep_intermediates ? &R.poleFlow[2] : nullptr, state, 2); });
+    poleJobs.push_back([&] { poleToSideFlow(rig, P, flipR, botSph, botWR, P.keep_intermediates ? &R.poleFlow[3] : nullptr, state, 3); });
   }
   runAll(poleJobs, P.threads);
+  if (state) { state->ovL = ovL; state->ovR = ovR; state->fLR = fLR; state->fRL = fRL; state->valid = true; }
   if (P.enable_top) {
     sphL = flattenLayersDeghostPreferBase(sphL, topWL);
     sphR = flattenLayersDeghostPreferBase(sphR, topWR);

@@ -282,6 +282,12 @@ class Context:
         names = ["total", "projection", "side_flow", "novel_view", "poles", "sharpen", "output"]
         return dict(zip(names, list(o)))
 
+    def set_temporal(self, on=True):
+        _check(lib().s360_ctx_set_temporal(self.h, int(on)))
+
+    def reset_temporal(self):
+        _check(lib().s360_ctx_reset_temporal(self.h))
+
     def set_graphs(self, on=True):
         _check(lib().s360_ctx_set_graphs(self.h, int(on)))
 

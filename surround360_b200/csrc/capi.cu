@@ -8,7 +8,7 @@
 
 using namespace s360;
 
-namespace s360 { void initContextTables(s360_ctx* c); void resetPlan(s360_ctx* c); }
+namespace s360 { void initContextTables(s360_ctx* c); void resetPlan(s360_ctx* c); void resetTemporal(s360_ctx* c); }
 
 static thread_local std::string g_lastError;
 #define S360_API_BEGIN try {
@@ -77,6 +77,19 @@ int s360_ctx_set_keep_intermediates(s360_ctx* c, int on) {
   S360_API_END
 }
 
+int s360_ctx_set_temporal(s360_ctx* c, int on) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  c->temporal = on != 0;
+  resetTemporal(c);
+  S360_API_END
+}
+int s360_ctx_reset_temporal(s360_ctx* c) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  resetTemporal(c);
+  S360_API_END
+}
 int s360_ctx_set_graphs(s360_ctx* c, int on) {
   S360_API_BEGIN
   require(c != nullptr, "null context");

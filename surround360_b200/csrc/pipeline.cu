@@ -195,6 +195,10 @@ struct FramePlan {
   DeviceBuffer prA, prB, prC, prFlow, prScratch;   // pole removal work images (imgW x imgH)
   std::unique_ptr<FlowBatch> prFlowBatch;
   bool poleRemoval = false;
+  // temporal regularisation across consecutive frames (video mode): previous projections, flows and
+  // extended fisheye images stay on the device instead of going through .bin / PNG files
+  bool temporal = false, prevValid = false;
+  DeviceBuffer prevProj, prevFlowSide, prevExtFish, prevPoleFlow;
   DeviceBuffer extSide, extFish;    // [nPole][poleH][extW]
   DeviceBuffer featherScratch;
   DeviceBuffer poleFlow;            // [nPole][poleH][extW] float2
@@ -207,13 +211,16 @@ struct FramePlan {
   std::unique_ptr<FlowBatch> sideFlow, poleFlowBatch;
   cudaEvent_t ev[8];
   cudaGraphExec_t graphExec = nullptr;
-  bool graphHasCube = false, lastWasTimed = false;
+  bool graphHasCube = false, graphUsesPrev = false, lastWasTimed = false;
   unsigned long long graphLaunches = 0;
   bool valid = false;
   ~FramePlan() { if (graphExec) cudaGraphExecDestroy(graphExec); }
 };
 
 static bool sameParams(const s360_params& a, const s360_params& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
+static bool planMatches(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
+  return c->plan && sameParams(c->plan->P, P) && c->plan->imgW == imgW && c->plan->imgH == imgH && c->plan->temporal == c->temporal;
+}
 
 static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
   if (!c->rigLoaded) throw std::runtime_error("no rig loaded");
@@ -256,7 +263,9 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
   F.panoL.alloc(eqPx * 4); F.panoR.alloc(eqPx * 4);
   S360_CUDA_CHECK(cudaMemsetAsync(F.panoL.p, 0, eqPx * 4, st));
   S360_CUDA_CHECK(cudaMemsetAsync(F.panoR.p, 0, eqPx * 4, st));
-  F.sideFlow = std::make_unique<FlowBatch>(2 * F.numCams, g.overlapW, g.camH, sideFP);
+  F.temporal = c->temporal;
+  F.sideFlow = std::make_unique<FlowBatch>(2 * F.numCams, g.overlapW, g.camH, sideFP, F.temporal);
+  if (F.temporal) { F.prevProj.alloc(F.proj.bytes); F.prevFlowSide.alloc(F.flowSide.bytes); }
   if (F.nPole) {
     if (g.poleH > P.eqr_height) throw std::runtime_error("pole image taller than the equirect");
     const size_t polePx = (size_t)P.eqr_width * g.poleH, extPx = (size_t)g.extW * g.poleH;
@@ -265,7 +274,8 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
     F.featherScratch.alloc(featherScratchBytes(P.eqr_width, g.poleH));
     F.poleFlow.alloc(extPx * 8 * F.nPole);
     F.poleWarped.alloc(polePx * 4 * F.nPole);
-    F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP);
+    F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP, F.temporal);
+    if (F.temporal) { F.prevExtFish.alloc(F.extFish.bytes); F.prevPoleFlow.alloc(F.poleFlow.bytes); }
     (void)c->blurKernelFor(P.std_alpha_feather_size);  // allocate now: nothing may allocate while a frame is captured
     F.poleRemoval = F.bottom && P.enable_pole_removal != 0;
     if (F.poleRemoval) {
@@ -308,6 +318,7 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
   const int eqW = P.eqr_width, eqH = P.eqr_height;
   auto stageEvent = [&](int i) { if (timed) S360_CUDA_CHECK(cudaEventRecord(F.ev[i], st)); };
   stageEvent(0);
+  const bool usePrev = F.temporal && F.prevValid;
   F.sideFlow->enableProfile(timed && c->profile);
   if (F.poleFlowBatch) F.poleFlowBatch->enableProfile(timed && c->profile);
 
@@ -370,7 +381,17 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
       ip.i0[i] = ovL; ip.i1[i] = ovR; ip.hint[i] = S360_HINT_LEFT;                           // flowLtoR
       ip.i0[F.numCams + i] = ovR; ip.i1[F.numCams + i] = ovL; ip.hint[F.numCams + i] = S360_HINT_RIGHT;  // flowRtoL
       ip.pitch0[i] = ip.pitch1[i] = ip.pitch0[F.numCams + i] = ip.pitch1[F.numCams + i] = g.camW;
+      if (usePrev) {  // TRSP:210-244, NovelView.cpp:282-297: previous flow of the same direction, previous I1 image
+        const uchar4* pproj = F.prevProj.as<uchar4>();
+        const size_t per = (size_t)g.overlapW * g.camH;
+        pv.prevFlow[i] = F.prevFlowSide.as<float2>() + (size_t)i * per;
+        pv.prevI1[i] = pproj + (size_t)r * g.camW * g.camH;                                        // previous overlap R
+        pv.prevFlow[F.numCams + i] = F.prevFlowSide.as<float2>() + (size_t)(F.numCams + i) * per;
+        pv.prevI1[F.numCams + i] = pproj + (size_t)i * g.camW * g.camH + (g.camW - g.overlapW);   // previous overlap L
+        pv.prevPitch[i] = pv.prevPitch[F.numCams + i] = g.camW;
+      }
     }
+    pv.enabled = usePrev;
     F.sideFlow->run(st, ip, pv, F.flowSide.as<float2>());
   }
   stageEvent(2);
@@ -410,8 +431,14 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
                           F.featherScratch.as<uint8_t>());
       launchExtendWrap(st, s.isTop ? F.topSph.as<uchar4>() : F.botSph.as<uchar4>(), eqW, g.poleH, extFish, g.extW);
       ip.i0[k] = extSide; ip.i1[k] = extFish; ip.pitch0[k] = ip.pitch1[k] = g.extW; ip.hint[k] = S360_HINT_DOWN;
+      if (usePrev) {  // TRSP:418-447
+        pv.prevFlow[k] = F.prevPoleFlow.as<float2>() + (size_t)k * extPx;
+        pv.prevI1[k] = F.prevExtFish.as<uchar4>() + (size_t)k * extPx;
+        pv.prevPitch[k] = g.extW;
+      }
       ++k;
     }
+    pv.enabled = usePrev;
     F.poleFlowBatch->run(st, ip, pv, F.poleFlow.as<float2>());
     k = 0;
     for (const Slot& s : slots) {
@@ -424,6 +451,14 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
       launchPoleWarp(st, a, c->rt);
       (s.isTop ? topLayer : botLayer)[s.eye] = a.warped;
       ++k;
+    }
+  }
+  if (F.temporal) {  // what the next frame's flows regularise against
+    S360_CUDA_CHECK(cudaMemcpyAsync(F.prevProj.p, F.proj.p, F.proj.bytes, cudaMemcpyDeviceToDevice, st));
+    S360_CUDA_CHECK(cudaMemcpyAsync(F.prevFlowSide.p, F.flowSide.p, F.flowSide.bytes, cudaMemcpyDeviceToDevice, st));
+    if (F.nPole) {
+      S360_CUDA_CHECK(cudaMemcpyAsync(F.prevExtFish.p, F.extFish.p, F.extFish.bytes, cudaMemcpyDeviceToDevice, st));
+      S360_CUDA_CHECK(cudaMemcpyAsync(F.prevPoleFlow.p, F.poleFlow.p, F.poleFlow.bytes, cudaMemcpyDeviceToDevice, st));
     }
   }
   // flatten (or plain copy when no poles): eye = BGRA panorama with the pole layers merged
@@ -471,9 +506,11 @@ static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
   if (!useGraph) {
     enqueueFrame(c, dev.data(), F.outEq.as<uint8_t>(), cube, true);
     F.lastWasTimed = true;
+    if (F.temporal) F.prevValid = true;
     return;
   }
-  if (!F.graphExec || F.graphHasCube != wantCube) {
+  const bool usePrevNow = F.temporal && F.prevValid;
+  if (!F.graphExec || F.graphHasCube != wantCube || F.graphUsesPrev != usePrevNow) {
     if (F.graphExec) { cudaGraphExecDestroy(F.graphExec); F.graphExec = nullptr; }
     const unsigned long long before = g_launchCount;
     cudaGraph_t graph = nullptr;
@@ -491,15 +528,17 @@ static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
     S360_CUDA_CHECK(cudaGraphInstantiate(&F.graphExec, graph, 0));
     cudaGraphDestroy(graph);
     F.graphHasCube = wantCube;
+    F.graphUsesPrev = usePrevNow;
   }
   S360_CUDA_CHECK(cudaGraphLaunch(F.graphExec, st));
   g_launchCount += F.graphLaunches;
   F.lastWasTimed = false;
+  if (F.temporal) F.prevValid = true;
 }
 
 void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* imagesDev, int imgW, int imgH, uint8_t* equirectDev,
                        uint8_t* cubemapDev) {
-  if (!c->plan || !sameParams(c->plan->P, P) || c->plan->imgW != imgW || c->plan->imgH != imgH) buildPlan(c, P, imgW, imgH);
+  if (!planMatches(c, P, imgW, imgH)) buildPlan(c, P, imgW, imgH);
   FramePlan& F = *c->plan;
   cudaStream_t st = c->stream;
   const size_t imgBytes = (size_t)imgW * imgH * 3;
@@ -517,7 +556,7 @@ void renderFrameDevice(s360_ctx* c, const s360_params& P, const uint8_t* const* 
 
 void renderFrameHost(s360_ctx* c, const s360_params& P, const uint8_t* const* images, int imgW, int imgH, uint8_t* equirect,
                      uint8_t* cubemap) {
-  if (!c->plan || !sameParams(c->plan->P, P) || c->plan->imgW != imgW || c->plan->imgH != imgH) buildPlan(c, P, imgW, imgH);
+  if (!planMatches(c, P, imgW, imgH)) buildPlan(c, P, imgW, imgH);
   FramePlan& F = *c->plan;
   cudaStream_t st = c->stream;
   const size_t imgBytes = (size_t)imgW * imgH * 3;
@@ -642,6 +681,7 @@ void poleToSide(s360_ctx* c, const s360_params& P, const uint8_t* sideHost, int 
 
 namespace s360 {
 void resetPlan(s360_ctx* c) { c->plan.reset(); }
+void resetTemporal(s360_ctx* c) { if (c->plan) c->plan->prevValid = false; }
 void collectProfile(s360_ctx* c) {
   if (!c->plan) return;
   S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));

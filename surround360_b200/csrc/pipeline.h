@@ -53,6 +53,7 @@ struct s360_ctx {
   bool keepIntermediates = false;
   bool profile = false;
   bool useGraphs = true;
+  bool temporal = false;
   s360::FlowBatch::SweepProfile sweepProfile;
   float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   std::string idScratch;

@@ -39,6 +39,7 @@ def lib():
         L = C.CDLL(so)
         L.o_rig_from_json.restype = C.c_void_p
         L.o_render_frame.restype = C.c_void_p
+        L.o_state_new.restype = C.c_void_p
         L.o_last_error.restype = C.c_char_p
         L.o_camera_id.restype = C.c_char_p
         L.o_camera_get_fov.restype = C.c_double
@@ -126,17 +127,27 @@ class Rig:
                              P(warped), P(flow))
         return warped, flow
 
-    def render_frame(self, images, p, pole_masks=None):
+    def render_frame(self, images, p, pole_masks=None, state=None):
         ims = [_c(i, np.uint8) for i in images]
         arr = (C.c_void_p * len(ims))(*[i.ctypes.data for i in ims])
         m1 = m2 = None
         if pole_masks is not None:
             m1, m2 = _c(pole_masks[0], np.uint8), _c(pole_masks[1], np.uint8)
         h = lib().o_render_frame(self.h, arr, ims[0].shape[1], ims[0].shape[0], C.byref(p), P(m1) if m1 is not None else None,
-                                 P(m2) if m2 is not None else None)
+                                 P(m2) if m2 is not None else None, state.h if state is not None else None)
         if not h:
             raise RuntimeError(lib().o_last_error().decode())
         return FrameResult(C.c_void_p(h))
+
+
+class FrameState:
+    """Temporal state carried from one rendered frame to the next (video mode)."""
+
+    def __init__(self):
+        self.h = C.c_void_p(lib().o_state_new())
+
+    def __del__(self):
+        lib().o_state_free(self.h)
 
 
 class FrameResult:

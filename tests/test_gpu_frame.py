@@ -175,3 +175,25 @@ def test_pole_removal(ctx, orig, frames17):
     with pytest.raises(api.VrCamException, match="missing or bad pole mask"):
         c2.renderStereoPanorama(api.default_params(**kw), frames17)
     c2.close()
+
+
+def test_temporal_chain_of_frames(orig, frames17):
+    """Video mode: frame i regularises against frame i-1 (flows + images kept on the device)."""
+    from conftest import RIG17
+    c = api.Context(0)
+    c.load_rig(RIG17)
+    c.set_temporal(True)
+    kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1024, final_eqr_height=1024, enable_top=1, enable_bottom=1, sharpening=0.25)
+    seq = [frames17, [np.ascontiguousarray(np.roll(im, 5, axis=1)) for im in frames17], frames17]
+    state = ob.FrameState()
+    outs = []
+    for fr in seq:
+        eq = c.renderStereoPanorama(api.default_params(**kw), fr)
+        ref = orig.render_frame(fr, ob.make_params(**kw), state=state)
+        close(eq, ref.get("equirect"), "equirect (temporal chain)")
+        outs.append(eq.copy())
+    assert not np.array_equal(outs[0], outs[2])      # same input, different history -> different result
+    c.reset_temporal()
+    eq = c.renderStereoPanorama(api.default_params(**kw), seq[0])
+    assert np.array_equal(eq, outs[0])               # after a reset the first frame renders like NONE again
+    c.close()
