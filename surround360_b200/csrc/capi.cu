@@ -69,7 +69,7 @@ int s360_ctx_synchronize(s360_ctx* c) {
   S360_API_END
 }
 void* s360_ctx_stream(s360_ctx* c) { return c ? (void*)c->stream : nullptr; }
-unsigned long long s360_ctx_launch_count(s360_ctx* c) { (void)c; return g_launchCount; }
+unsigned long long s360_ctx_launch_count(s360_ctx* c) { (void)c; return g_launchCount.load(); }
 int s360_ctx_set_keep_intermediates(s360_ctx* c, int on) {
   S360_API_BEGIN
   require(c != nullptr, "null context");

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <vector>
 #include "common.cuh"
 #include "remap.cuh"
@@ -10,7 +11,7 @@
 namespace s360 {
 
 // global launch counter (bench.py "gpu_launches")
-extern unsigned long long g_launchCount;
+extern std::atomic<unsigned long long> g_launchCount;
 
 // ---------------- warp_kernels.cu ----------------
 // BGR8/BGRA8 host-layout source -> BGRA8 with alpha 255 (or source alpha) and the
@@ -151,7 +152,6 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   void collectProfile(SweepProfile* acc);
 
  private:
-  struct Impl;
   int n_, w_, h_, dw_, dh_;
   FlowParams P_;
   std::vector<int> lw_, lh_;

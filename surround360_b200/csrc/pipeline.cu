@@ -512,7 +512,7 @@ static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
   const bool usePrevNow = F.temporal && F.prevValid;
   if (!F.graphExec || F.graphHasCube != wantCube || F.graphUsesPrev != usePrevNow) {
     if (F.graphExec) { cudaGraphExecDestroy(F.graphExec); F.graphExec = nullptr; }
-    const unsigned long long before = g_launchCount;
+    const unsigned long long before = g_launchCount.load();
     cudaGraph_t graph = nullptr;
     S360_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     try {
@@ -523,8 +523,8 @@ static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
       throw;
     }
     S360_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
-    F.graphLaunches = g_launchCount - before;
-    g_launchCount = before;  // nothing has run yet; replays are counted below
+    F.graphLaunches = g_launchCount.load() - before;
+    g_launchCount -= F.graphLaunches;  // nothing has run yet; replays are counted below
     S360_CUDA_CHECK(cudaGraphInstantiate(&F.graphExec, graph, 0));
     cudaGraphDestroy(graph);
     F.graphHasCube = wantCube;

@@ -8,7 +8,7 @@
 
 namespace s360 {
 
-unsigned long long g_launchCount = 0;
+std::atomic<unsigned long long> g_launchCount{0};
 
 static inline dim3 grid2d(int w, int h, dim3 b) { return dim3(iDivUp(w, b.x), iDivUp(h, b.y)); }
 
