@@ -28,6 +28,11 @@ import numpy as np
 METRIC = "8k_stereo_equirect_frames_per_sec"
 ALGO_BYTES_PER_LEVELPX_PER_SWEEP = 48.0  # "2 sweeps 96 B / level-px"
 OUT_MP_PER_FRAME = 8192 * 8192 / 1e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full capture
+# (profiles/sweep_r1_final_raw.csv: finest side level, 28 flows x 607x884, algorithmic 48 B x 15.02 Mpx = 721 MB)
+NCU_SWEEP_TRAFFIC_BYTES = 871.4e6
+NCU_SWEEP_TRAFFIC_NOTE = "ncu capture of the finest side-level launch (3.39 ms; algorithmic bytes of that launch: 721 MB); " \
+                         "`achieved` averages over all 134 sweep launches of a frame"
 
 
 def preset_kwargs(name, cubemap=False):
@@ -319,7 +324,8 @@ def main():
         bytes_per_launch = ALGO_BYTES_PER_LEVELPX_PER_SWEEP * prof["level_pixels"] / prof["launches"]
         achieved = bytes_per_launch / per_launch_s / 1e9
         roof = {"bound": "hbm", "kernel": "k_sweep (PixFlow wavefront sweep, forward+backward)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_SWEEP_TRAFFIC_BYTES, "traffic_note": NCU_SWEEP_TRAFFIC_NOTE,
+                "peak_source": peak_src,
                 "avg_launch_ms": prof["ms"] / prof["launches"], "launches_timed": prof["launches"],
                 "ns_per_wavefront_step": 1e6 * prof["ms"] / max(prof["steps"], 1.0),
                 "sweep_ms_per_frame": prof["ms"] / args.steps, "instrumented_pass_ms_per_step": ms_prof / args.steps,
