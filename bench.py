@@ -150,12 +150,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--preset", default="8k", choices=["3k", "4k", "6k", "8k"])
     ap.add_argument("--cubemap", action="store_true", help="config 5: also produce the 1536^2 cubemap strip")
-    ap.add_argument("--inflight", type=int, default=10, help="frames in flight per GPU (contexts/streams)")
+    ap.add_argument("--inflight", type=int, default=20, help="frames in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -182,7 +182,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     F = max(1, args.inflight)
-    ctxs = [api.Context(local_rank) for _ in range(F)]
+    ctxs = [api.Context(local_rank)]
     # rig: parsed on rank 0, one NCCL broadcast of the serialised tables, every rank deserialises
     rig_path = f"/tmp/s360_bench_rig_{rank}.json"
     rig_gen.write_rig(rig_path)
@@ -198,13 +198,26 @@ def main():
             blob = torch.zeros(int(size.item()), device=dev, dtype=torch.uint8)
         dist.broadcast(blob, 0)
     blob_host = blob.cpu().numpy()
-    for c in ctxs:
-        c.load_rig_blob(blob_host)
+    ctxs[0].load_rig_blob(blob_host)
 
     params = api.default_params(**preset_kwargs(args.preset, args.cubemap))
     eq_w, eq_h, cw, ch = ctxs[0].output_size(params)
     n_sets = 2
     frame_sets = make_frames(rig_path, n_sets)
+    # frames in flight are bounded by HBM: build the first context's plan, measure what it took and keep
+    # 12 % of the device free
+    free0, total_mem = torch.cuda.mem_get_info(dev)
+    ctxs[0].renderStereoPanorama(params, frame_sets[0])
+    free1, _ = torch.cuda.mem_get_info(dev)
+    per_ctx = max(free0 - free1, 1)
+    fit = int((free1 - 0.12 * total_mem) // per_ctx) + 1
+    if fit < F:
+        print(f"[bench] {F} frames in flight do not fit ({per_ctx / 2**30:.1f} GiB per context): using {max(fit, 1)}", file=sys.stderr)
+        F = max(fit, 1)
+    for _ in range(F - 1):
+        c = api.Context(local_rank)
+        c.load_rig_blob(blob_host)
+        ctxs.append(c)
     img_h, img_w = frame_sets[0][0].shape[:2]
     n_cam = len(frame_sets[0])
     h2d_bytes = n_cam * img_w * img_h * 3

@@ -129,7 +129,10 @@ struct FlowPrevPtrs {  // optional temporal inputs
 class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved concurrently
  public:
   // temporal: allocate the previous-flow / motion pyramids; levelDump: allocate per-level dump planes
-  FlowBatch(int n, int w, int h, const FlowParams& p, bool temporal = false, bool levelDump = false);
+  // externalWorkspace: do not allocate; the owner calls bindWorkspace() with >= bytes() of device memory that
+  // may be shared with other batches which never run at the same time
+  FlowBatch(int n, int w, int h, const FlowParams& p, bool temporal = false, bool levelDump = false, bool externalWorkspace = false);
+  void bindWorkspace(void* ws, size_t bytes);
   ~FlowBatch();
   FlowBatch(const FlowBatch&) = delete;
   // flowOut: [n][h][w] float2 contiguous
@@ -174,6 +177,10 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *g1Scratch_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
   void* arena_ = nullptr;
+  void* boundaryAlloc_ = nullptr;
+  bool bound_ = false;
+  std::vector<size_t> oI0_, oI1_, oA0_, oA1_, oPrev_, oMot_, oDump_;
+  size_t oS0_ = 0, oS1_ = 0, oRec_ = 0, oQuad_ = 0, oD_ = 0, oFA_ = 0, oFull_ = 0, oFB_ = 0, oG1_ = 0, oTmp_ = 0;
 };
 
 }  // namespace s360

@@ -206,7 +206,9 @@ struct FramePlan {
   DeviceBuffer eyes;                // 2 x (eqrW x eqrH) uchar4, left then right
   uchar4* eye(int e, size_t eqPx) const { return eyes.as<uchar4>() + (size_t)e * eqPx; }
   DeviceBuffer eyePre[2];           // copy before sharpening (keepIntermediates)
-  DeviceBuffer sharpF, sharpLp;
+  DeviceBuffer workspace;           // shared by the flow batches and the sharpen scratch (never concurrent)
+  float* sharpF = nullptr;
+  uchar4* sharpLp = nullptr;
   DeviceBuffer outEq, outCube;      // device outputs for the host variant
   std::unique_ptr<FlowBatch> sideFlow, poleFlowBatch;
   cudaEvent_t ev[8];
@@ -264,7 +266,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
   S360_CUDA_CHECK(cudaMemsetAsync(F.panoL.p, 0, eqPx * 4, st));
   S360_CUDA_CHECK(cudaMemsetAsync(F.panoR.p, 0, eqPx * 4, st));
   F.temporal = c->temporal;
-  F.sideFlow = std::make_unique<FlowBatch>(2 * F.numCams, g.overlapW, g.camH, sideFP, F.temporal);
+  F.sideFlow = std::make_unique<FlowBatch>(2 * F.numCams, g.overlapW, g.camH, sideFP, F.temporal, false, true);
   if (F.temporal) { F.prevProj.alloc(F.proj.bytes); F.prevFlowSide.alloc(F.flowSide.bytes); }
   if (F.nPole) {
     if (g.poleH > P.eqr_height) throw std::runtime_error("pole image taller than the equirect");
@@ -274,7 +276,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
     F.featherScratch.alloc(featherScratchBytes(P.eqr_width, g.poleH));
     F.poleFlow.alloc(extPx * 8 * F.nPole);
     F.poleWarped.alloc(polePx * 4 * F.nPole);
-    F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP, F.temporal);
+    F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP, F.temporal, false, true);
     if (F.temporal) { F.prevExtFish.alloc(F.extFish.bytes); F.prevPoleFlow.alloc(F.poleFlow.bytes); }
     (void)c->blurKernelFor(P.std_alpha_feather_size);  // allocate now: nothing may allocate while a frame is captured
     F.poleRemoval = F.bottom && P.enable_pole_removal != 0;
@@ -285,11 +287,22 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
       const size_t ipx = (size_t)imgW * imgH;
       F.prA.alloc(ipx * 4); F.prB.alloc(ipx * 4); F.prC.alloc(ipx * 4); F.prFlow.alloc(ipx * 8);
       F.prScratch.alloc(featherScratchBytes(imgW, imgH));
-      F.prFlowBatch = std::make_unique<FlowBatch>(1, imgW, imgH, prFP);
+      F.prFlowBatch = std::make_unique<FlowBatch>(1, imgW, imgH, prFP, false, false, true);
     }
   }
   F.eyes.alloc(eqPx * 4 * 2);   // both eyes back to back so one launch sharpens them together
-  if (P.sharpening > 0.0f) { F.sharpF.alloc(eqPx * 3 * 4 * 2); F.sharpLp.alloc(eqPx * 4 * 2 * 2); }
+  // One workspace for everything that never runs at the same time within a frame (one stream): the side, pole
+  // and pole-removal flow batches and the sharpen scratch.
+  const size_t sharpBytes = P.sharpening > 0.0f ? eqPx * 3 * 4 * 2 + eqPx * 4 * 2 * 2 : 0;
+  size_t wsBytes = std::max(F.sideFlow->bytes(), sharpBytes);
+  if (F.poleFlowBatch) wsBytes = std::max(wsBytes, F.poleFlowBatch->bytes());
+  if (F.prFlowBatch) wsBytes = std::max(wsBytes, F.prFlowBatch->bytes());
+  F.workspace.alloc(wsBytes);
+  F.sideFlow->bindWorkspace(F.workspace.p, wsBytes);
+  if (F.poleFlowBatch) F.poleFlowBatch->bindWorkspace(F.workspace.p, wsBytes);
+  if (F.prFlowBatch) F.prFlowBatch->bindWorkspace(F.workspace.p, wsBytes);
+  F.sharpF = F.workspace.as<float>();
+  F.sharpLp = reinterpret_cast<uchar4*>(F.workspace.as<uint8_t>() + eqPx * 3 * 4 * 2);
   for (auto& e : F.ev) S360_CUDA_CHECK(cudaEventCreate(&e));
   F.valid = true;
   c->plan = std::move(plan);
@@ -473,7 +486,7 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
       S360_CUDA_CHECK(cudaMemcpyAsync(F.eyePre[e].p, F.eye(e, (size_t)eqW * eqH), (size_t)eqW * eqH * 4, cudaMemcpyDeviceToDevice, st));
     }
   if (P.sharpening > 0.0f)
-    launchSharpen(st, F.eyes.as<uchar4>(), eqW, eqH, 2, (float)(1.0f + P.sharpening), F.sharpF.as<float>(), F.sharpLp.as<uchar4>());
+    launchSharpen(st, F.eyes.as<uchar4>(), eqW, eqH, 2, (float)(1.0f + P.sharpening), F.sharpF, F.sharpLp);
   stageEvent(5);
 
   // ---- cubemap + final equirect (TRSP:915-961) ----
