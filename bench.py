@@ -4,9 +4,9 @@
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 17-camera
 rig, 2048x2048 synthetic frames -> 8K stereo (left over right) equirect, batch_process_video's
 "8k" preset (eqr 8400x4096 -> 8192x8192, sharpening 0.25), --enable_top --enable_bottom,
-pixflow_low, prev_frame_data_dir NONE. A step = one frame. Frames are independent, so with
-N GPUs each rank renders its own frames (weak scaling); the only collective is one NCCL
-broadcast of the serialised rig at start-up.
+pixflow_low, prev_frame_data_dir NONE. A step = one batch of F independent frames (F = frames in flight per GPU, up to 20, bounded by
+free HBM); `value` is frames/s. With N GPUs each rank renders its own batches (weak scaling); the
+only collective is one NCCL broadcast of the serialised rig at start-up.
 
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
   python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port) on host cores
@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--preset", default="8k", choices=["3k", "4k", "6k", "8k"])
@@ -244,7 +244,9 @@ def main():
         if world > 1:
             dist.barrier()
 
-    for s in range(max(args.warmup, F)):   # warm-up also builds every context's plan and captures its frame graph
+    # A step = one batch of F frames (one per context in flight), so that the measured throughput does not depend
+    # on how many steps the caller asks for. Warm-up batches also build every context's plan and frame graph.
+    for s in range(max(args.warmup, 1) * F):
         enqueue(s)
     sync_all()
 
@@ -273,12 +275,13 @@ def main():
     # pass A: the measured throughput (whole-frame CUDA-graph replay, no instrumentation)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, launches, t_enq = timed_pass(args.steps)
+    ms, launches, t_enq = timed_pass(args.steps * F)
     clocks = sampler.stop()
     # pass B: the same region with CUDA events around every sweep launch (plain launch path) for the roofline block
     for c in ctxs:
         c.profile_enable(True)
-    ms_prof, _, _ = timed_pass(args.steps)
+    prof_steps = min(args.steps, 2)
+    ms_prof, _, _ = timed_pass(prof_steps * F)
     prof = dict(ms=0.0, launches=0, level_pixels=0.0, steps=0.0)
     for c in ctxs:
         pr = c.profile_sweep()
@@ -289,7 +292,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * args.steps / (ms_max / 1000.0)
+    value = world * args.steps * F / (ms_max / 1000.0)
 
     # stage breakdown of one frame alone on the device (host API fills the stage timers)
     pinned_in = [[torch.from_numpy(im).pin_memory() for im in fs] for fs in frame_sets]
@@ -316,14 +319,14 @@ def main():
         run_threads(F)  # warm
         barrier(); sync_all()
         t0 = time.perf_counter()
-        run_threads(args.steps)
+        run_threads(args.steps * F)
         sync_all()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * args.steps / float(tt.item()), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": d2h_bytes}
+        e2e = {"value": world * args.steps * F / float(tt.item()), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * F,
+               "d2h_bytes_per_step": d2h_bytes * F}
 
     if rank != 0:
         if world > 1:
@@ -341,7 +344,7 @@ def main():
                 "peak_source": peak_src,
                 "avg_launch_ms": prof["ms"] / prof["launches"], "launches_timed": prof["launches"],
                 "ns_per_wavefront_step": 1e6 * prof["ms"] / max(prof["steps"], 1.0),
-                "sweep_ms_per_frame": prof["ms"] / args.steps, "instrumented_pass_ms_per_step": ms_prof / args.steps,
+                "sweep_ms_per_frame": prof["ms"] / (prof_steps * F), "instrumented_pass_ms_per_step": ms_prof / prof_steps,
                 "note": "dependency-latency-bound recurrence: reported against the HBM roofline for completeness"}
 
     cpu_baseline = None
@@ -360,16 +363,16 @@ def main():
                         "sample": f"1 frame of the '6k' preset ({dt:.1f} s wall, reference threading shape), converted to 8K frames/s by output megapixels"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, F),
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32", "data": "synthetic",
         "config": {"workload": f"17-cam rig, 2048x2048 synthetic frames -> 8K stereo equirect ({args.preset} preset, top+bottom, pixflow_low"
                                + (", +cubemap 1536" if args.cubemap else "") + ")",
-                   "frames_in_flight_per_gpu": F, "l2": "inputs (214 MB/frame) exceed the 126 MB L2; two alternating input sets",
+                   "frames_per_step": F, "frames_in_flight_per_gpu": F, "l2": "inputs (214 MB/frame) exceed the 126 MB L2; two alternating input sets",
                    "parallelism": f"frames sharded one-per-GPU x{world}, single NCCL broadcast of the rig"},
         "mp_per_s": value * eq_w * eq_h / 1e6,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline,
-        "stage_ms_single_frame": stage_ms, "host_enqueue_ms_per_frame": 1000.0 * t_enq / args.steps,
+        "stage_ms_single_frame": stage_ms, "host_enqueue_ms_per_frame": 1000.0 * t_enq / (args.steps * F),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
