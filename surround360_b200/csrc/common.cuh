@@ -55,6 +55,8 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 
 #endif  // __CUDACC__
 
+inline double resizeScale(int ssize, int dsize) { return 1. / ((double)dsize / (double)ssize); }
+
 // cv interpolateCubic (A = -0.75); float, op order as written
 __host__ __device__ __forceinline__ void cubicCoeffs(float x, float* k) {
   const float A = -0.75f;
@@ -65,9 +67,10 @@ __host__ __device__ __forceinline__ void cubicCoeffs(float x, float* k) {
 }
 
 #ifdef __CUDACC__
-// cv::resize source coordinate: f = (float)((d+0.5)*scale - 0.5), scale = 1/((double)dsize/ssize)
-__device__ __forceinline__ void resizeCoord(int d, int ssize, int dsize, int& s, float& f) {
-  const double scale = 1. / ((double)dsize / (double)ssize);
+// cv::resize source coordinate: f = (float)((d+0.5)*scale - 0.5), scale = 1/((double)dsize/ssize).
+// The scale is the same for every pixel of a launch: the host evaluates it (resizeScale below, same
+// IEEE double operations) and passes it in, which keeps two fp64 divisions out of every thread.
+__device__ __forceinline__ void resizeCoord(int d, double scale, int& s, float& f) {
   f = (float)((d + 0.5) * scale - 0.5);
   s = cvFloorF(f);
   f -= (float)s;

@@ -53,6 +53,74 @@ __global__ void k_blur8_cols_extend(const uint16_t* __restrict__ t, int w, int h
   c.w = (unsigned char)min((s + (1u << 15)) >> 16, 255u);
   for (int xx = x; xx < extW; xx += w) ext[(size_t)y * extW + xx] = c;
 }
+// Fast paths for the default 31-tap kernel (exact integer arithmetic: any evaluation order gives the
+// same sums). Rows: a block stages 8 rows x (128 + 30) samples as ints; a thread produces 4
+// neighbouring outputs from 34 staged values. Columns: a thread owns one column of a 16-row strip and
+// keeps the 46 rows it needs in registers.
+constexpr int kB8N = 31, kB8R = 15, kB8TileW = 128, kB8Strip = 16;
+__global__ void __launch_bounds__(256)
+k_blur8_rows31(const uint8_t* __restrict__ a, int w, int h, const int* __restrict__ fk, uint16_t* __restrict__ out) {
+  __shared__ __align__(16) int sm[8][kB8TileW + 32];
+  __shared__ int sk[kB8N + 1];
+  const int x0 = blockIdx.x * kB8TileW, y = blockIdx.y * 8 + threadIdx.y;
+  const uint8_t* row = a + (size_t)min(y, h - 1) * w;
+  for (int i = threadIdx.x; i < kB8TileW + 2 * kB8R; i += 32) {
+    const int xs = reflect101(min(x0 - kB8R + i, w + kB8R - 1), w);  // columns past w+14 feed no valid output
+    sm[threadIdx.y][i] = (int)__ldg(row + xs);
+  }
+  if (threadIdx.y == 0 && threadIdx.x < kB8N) sk[threadIdx.x] = __ldg(fk + threadIdx.x);
+  __syncthreads();
+  const int x = x0 + 4 * threadIdx.x;
+  if (y >= h || x >= w) return;
+  int v[36];
+  const int4* p = reinterpret_cast<const int4*>(&sm[threadIdx.y][4 * threadIdx.x]);
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int4 q = p[j];
+    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+  }
+  unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+  for (int t = 0; t < kB8N; ++t) {
+    const unsigned c = (unsigned)sk[t];
+    s0 += (unsigned)v[t] * c; s1 += (unsigned)v[t + 1] * c; s2 += (unsigned)v[t + 2] * c; s3 += (unsigned)v[t + 3] * c;
+  }
+  uint16_t* o = out + (size_t)y * w + x;
+  o[0] = (uint16_t)min(s0, 65535u);
+  if (x + 1 < w) o[1] = (uint16_t)min(s1, 65535u);
+  if (x + 2 < w) o[2] = (uint16_t)min(s2, 65535u);
+  if (x + 3 < w) o[3] = (uint16_t)min(s3, 65535u);
+}
+__global__ void __launch_bounds__(128)
+k_blur8_cols_extend31(const uint16_t* __restrict__ t, int w, int h, const int* __restrict__ fk, const uchar4* __restrict__ src, int srcH,
+                      int flip, uchar4* __restrict__ ext, int extW) {
+  __shared__ int sk[kB8N + 1];
+  if (threadIdx.x < kB8N) sk[threadIdx.x] = __ldg(fk + threadIdx.x);
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * kB8Strip;
+  if (x >= w) return;
+  unsigned v[kB8Strip + 2 * kB8R];
+#pragma unroll
+  for (int r = 0; r < kB8Strip + 2 * kB8R; ++r) {
+    const int yy = reflect101(min(y0 - kB8R + r, h + kB8R - 1), h);  // rows past h+14 feed no valid output
+    v[r] = (unsigned)__ldg(t + (size_t)yy * w + x);
+  }
+  unsigned c[kB8N];
+#pragma unroll
+  for (int j = 0; j < kB8N; ++j) c[j] = (unsigned)sk[j];
+#pragma unroll
+  for (int i = 0; i < kB8Strip; ++i) {
+    const int y = y0 + i;
+    if (y < h) {
+      unsigned s = 0;
+#pragma unroll
+      for (int j = 0; j < kB8N; ++j) s += v[i + j] * c[j];
+      uchar4 px = readMaybeFlipped(src, w, srcH, flip, x, y);
+      px.w = (unsigned char)min((s + (1u << 15)) >> 16, 255u);
+      for (int xx = x; xx < extW; xx += w) ext[(size_t)y * extW + xx] = px;
+    }
+  }
+}
 size_t featherScratchBytes(int w, int rows) { return (size_t)w * rows * 2 + (size_t)w * rows * 2 + 256; }
 void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, int rows, int flip, int erodeSize,
                          const int* blurKernelFixed, uchar4* extOut, int extW, uint8_t* scratch) {
@@ -63,8 +131,13 @@ void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, in
   uint16_t* t = reinterpret_cast<uint16_t*>(scratch + 2 * plane);
   k_extract_alpha<<<grid2d(w, rows, b), b, 0, st>>>(src, w, srcH, rows, flip, a0);
   k_erode_cross<<<grid2d(w, rows, b), b, 0, st>>>(a0, w, rows, erodeSize, a1);
-  k_blur8_rows<<<grid2d(w, rows, b), b, 0, st>>>(a1, w, rows, blurKernelFixed, erodeSize, t);
-  k_blur8_cols_extend<<<grid2d(w, rows, b), b, 0, st>>>(t, w, rows, blurKernelFixed, erodeSize, src, srcH, flip, extOut, extW);
+  if (erodeSize == kB8N) {
+    k_blur8_rows31<<<dim3(iDivUp(w, kB8TileW), iDivUp(rows, 8)), b, 0, st>>>(a1, w, rows, blurKernelFixed, t);
+    k_blur8_cols_extend31<<<dim3(iDivUp(w, 128), iDivUp(rows, kB8Strip)), 128, 0, st>>>(t, w, rows, blurKernelFixed, src, srcH, flip, extOut, extW);
+  } else {
+    k_blur8_rows<<<grid2d(w, rows, b), b, 0, st>>>(a1, w, rows, blurKernelFixed, erodeSize, t);
+    k_blur8_cols_extend<<<grid2d(w, rows, b), b, 0, st>>>(t, w, rows, blurKernelFixed, erodeSize, src, srcH, flip, extOut, extW);
+  }
   g_launchCount += 4;
 }
 void launchFeatherAlpha(cudaStream_t st, const uchar4* src, int w, int h, int erodeSize, const int* blurKernelFixed, uchar4* dst,

@@ -261,9 +261,9 @@ void launchPoleWarp(cudaStream_t st, const PoleWarpArgs& a, const RemapTables& r
 // float for element index (x*cn+c) < (dw*cn & ~7) (OpenCV's SIMD body) and exact integers
 // for the row tail. (PixFlow.h:98-99 with cn=4, TRSP:943-956 with cn=3.)
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void cubicTaps11(int d, int ssize, int dsize, int& s, int* c) {
+__device__ __forceinline__ void cubicTaps11(int d, double scale, int& s, int* c) {
   float f;
-  resizeCoord(d, ssize, dsize, s, f);
+  resizeCoord(d, scale, s, f);
   float k[4];
   cubicCoeffs(f, k);
 #pragma unroll
@@ -272,12 +272,12 @@ __device__ __forceinline__ void cubicTaps11(int d, int ssize, int dsize, int& s,
 template <int CN>
 __global__ void __launch_bounds__(256)
 k_resize_cubic8(const uchar4* __restrict__ src, int sw, int sh, int spitch, uchar4* __restrict__ dst, int dw, int dh, int dpitch,
-                uint8_t* __restrict__ dstPacked3) {
+                uint8_t* __restrict__ dstPacked3, double scaleX, double scaleY) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= dw || y >= dh) return;
   int sx, sy, ax[4], by[4];
-  cubicTaps11(x, sw, dw, sx, ax);
-  cubicTaps11(y, sh, dh, sy, by);
+  cubicTaps11(x, scaleX, sx, ax);
+  cubicTaps11(y, scaleY, sy, by);
   int rows[4][4];  // [tap row][channel]
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -316,8 +316,10 @@ k_resize_cubic8(const uchar4* __restrict__ src, int sw, int sh, int spitch, ucha
 void launchResizeCubic8(cudaStream_t st, const uchar4* src, int sw, int sh, int spitch, int cn, uchar4* dst, int dw, int dh, int dpitch,
                         uint8_t* dstPacked3) {
   dim3 b(32, 8);
-  if (cn == 4) k_resize_cubic8<4><<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, dstPacked3);
-  else k_resize_cubic8<3><<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, dstPacked3);
+  if (cn == 4) k_resize_cubic8<4><<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, dstPacked3, resizeScale(sw, dw),
+                                                                resizeScale(sh, dh));
+  else k_resize_cubic8<3><<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, dstPacked3, resizeScale(sw, dw),
+                                                                resizeScale(sh, dh));
   ++g_launchCount;
 }
 
