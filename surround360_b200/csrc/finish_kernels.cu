@@ -31,6 +31,79 @@ __global__ void k_erode_cross(const uint8_t* __restrict__ a, int w, int h, int r
   for (int xx = x0; xx <= x1; ++xx) m = min(m, (int)__ldg(row + xx));
   out[(size_t)y * w + x] = (uint8_t)m;
 }
+// Fast path for the default 63-wide cross (r = 31): the window minimum is built by doubling
+// (windows of 2, 4, ... 32 samples; 63 = two overlapping 32-windows), two windows per instruction
+// with the packed 16-bit minimum. k_erode_v31: a thread owns one column of a 32-row strip (94 rows
+// in registers). k_erode_h31: a block stages 32 rows x 190 columns in shared memory, a thread owns a
+// 32-column strip of one row, and the result is combined with the vertical minimum.
+constexpr int kErR = 31, kErStrip = 32;
+__device__ __forceinline__ void erodeWindows32(unsigned (&v)[2 * kErR + 1]) {
+  // in: v[i] = s[i] | s[i+31] << 16 for a strip of 94 samples s; out (i <= 31): v[i] = min s[i..i+31] | min s[i+31..i+62] << 16
+#pragma unroll
+  for (int sft = 1; sft <= 16; sft <<= 1) {
+#pragma unroll
+    for (int i = 0; i + sft < 2 * kErR + 1; ++i) v[i] = __vminu2(v[i], v[i + sft]);
+  }
+}
+__global__ void __launch_bounds__(128)
+k_erode_v31(const uint8_t* __restrict__ a, int w, int h, uint8_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * kErStrip;
+  if (x >= w) return;
+  unsigned v[2 * kErR + 1];
+#pragma unroll
+  for (int i = 0; i < 2 * kErR + 1; ++i) v[i] = 0;
+#pragma unroll
+  for (int r = 0; r < kErStrip + 2 * kErR; ++r) {
+    const int y = y0 - kErR + r;
+    const unsigned s = (y >= 0 && y < h) ? (unsigned)__ldg(a + (size_t)y * w + x) : 255u;  // outside the image: neutral
+    if (r <= 2 * kErR) v[r] |= s;
+    if (r >= kErR) v[r - kErR] |= s << 16;
+  }
+  erodeWindows32(v);
+#pragma unroll
+  for (int r = 0; r < kErStrip; ++r) {
+    const int y = y0 + r;
+    if (y < h) out[(size_t)y * w + x] = (uint8_t)min(v[r] & 0xffffu, v[r] >> 16);
+  }
+}
+constexpr int kErTileW = 128, kErPitch = 196;  // 49 words per staged row: odd, so the 32 rows of a warp hit 32 banks
+__global__ void __launch_bounds__(128)
+k_erode_h31(const uint8_t* __restrict__ a, const uint8_t* __restrict__ vmin, int w, int h, uint8_t* __restrict__ out) {
+  __shared__ uint8_t sIn[kErStrip * kErPitch];
+  __shared__ uint8_t sOut[kErStrip * (kErTileW + 4)];
+  const int x0 = blockIdx.x * kErTileW, y0 = blockIdx.y * kErStrip;
+  for (int i = threadIdx.x; i < kErStrip * (kErTileW + 2 * kErR); i += 128) {
+    const int r = i / (kErTileW + 2 * kErR), c = i - r * (kErTileW + 2 * kErR);
+    const int x = x0 - kErR + c, y = y0 + r;
+    sIn[r * kErPitch + c] = (x >= 0 && x < w && y < h) ? __ldg(a + (size_t)y * w + x) : (uint8_t)255;
+  }
+  __syncthreads();
+  {
+    const int r = threadIdx.x & 31, strip = threadIdx.x >> 5;
+    const uint8_t* rowp = sIn + r * kErPitch + strip * 32;
+    unsigned v[2 * kErR + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * kErR + 1; ++i) v[i] = 0;
+#pragma unroll
+    for (int c = 0; c < 32 + 2 * kErR; ++c) {
+      const unsigned s = rowp[c];
+      if (c <= 2 * kErR) v[c] |= s;
+      if (c >= kErR) v[c - kErR] |= s << 16;
+    }
+    erodeWindows32(v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sOut[r * (kErTileW + 4) + strip * 32 + j] = (uint8_t)min(v[j] & 0xffffu, v[j] >> 16);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kErStrip * kErTileW; i += 128) {
+    const int r = i / kErTileW, c = i - r * kErTileW;
+    const int x = x0 + c, y = y0 + r;
+    if (x < w && y < h) {
+      const size_t idx = (size_t)y * w + x;
+      out[idx] = (uint8_t)min((int)sOut[r * (kErTileW + 4) + c], (int)__ldg(vmin + idx));
+    }
+  }
+}
 __global__ void k_blur8_rows(const uint8_t* __restrict__ a, int w, int h, const int* __restrict__ fk, int n, uint16_t* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
@@ -130,7 +203,15 @@ void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, in
   uint8_t* a1 = scratch + plane;
   uint16_t* t = reinterpret_cast<uint16_t*>(scratch + 2 * plane);
   k_extract_alpha<<<grid2d(w, rows, b), b, 0, st>>>(src, w, srcH, rows, flip, a0);
-  k_erode_cross<<<grid2d(w, rows, b), b, 0, st>>>(a0, w, rows, erodeSize, a1);
+  if (erodeSize == kErR) {
+    // a1 <- vertical minimum; the u16 scratch `t` (unused until the blur) holds the final eroded plane, copied back to a1's role
+    uint8_t* vtmp = reinterpret_cast<uint8_t*>(t);
+    k_erode_v31<<<dim3(iDivUp(w, 128), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, w, rows, vtmp);
+    k_erode_h31<<<dim3(iDivUp(w, kErTileW), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, vtmp, w, rows, a1);
+    ++g_launchCount;
+  } else {
+    k_erode_cross<<<grid2d(w, rows, b), b, 0, st>>>(a0, w, rows, erodeSize, a1);
+  }
   if (erodeSize == kB8N) {
     k_blur8_rows31<<<dim3(iDivUp(w, kB8TileW), iDivUp(rows, 8)), b, 0, st>>>(a1, w, rows, blurKernelFixed, t);
     k_blur8_cols_extend31<<<dim3(iDivUp(w, 128), iDivUp(rows, kB8Strip)), 128, 0, st>>>(t, w, rows, blurKernelFixed, src, srcH, flip, extOut, extW);
