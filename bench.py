@@ -30,8 +30,8 @@ ALGO_BYTES_PER_LEVELPX_PER_SWEEP = 48.0  # "2 sweeps 96 B / leve
 OUT_MP_PER_FRAME = 8192 * 8192 / 1e6
 # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full capture
 # (profiles/sweep_r1_final_raw.csv: finest side level, 28 flows x 607x884, algorithmic 48 B x 15.02 Mpx = 721 MB)
-NCU_SWEEP_TRAFFIC_BYTES = 871.4e6
-NCU_SWEEP_TRAFFIC_NOTE = "ncu capture of the finest side-level launch (3.39 ms; algorithmic bytes of that launch: 721 MB); " \
+NCU_SWEEP_TRAFFIC_BYTES = 871.9e6
+NCU_SWEEP_TRAFFIC_NOTE = "ncu capture of the finest side-level launch (3.12 ms; algorithmic bytes of that launch: 721 MB); " \
                          "`achieved` averages over all 134 sweep launches of a frame"
 
 

@@ -49,12 +49,7 @@ int s360_ctx_create(int device, s360_ctx** out) {
   if (prop.major < 10) throw std::runtime_error(std::string("device '") + prop.name + "' is not sm_100a-class; kernels are built for B200 only");
   auto c = std::make_unique<s360_ctx>();
   c->device = device;
-  {
-    int lo = 0, hi = 0;
-    S360_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    const int prioMode = getenv("S360_PRIO") ? atoi(getenv("S360_PRIO")) : 0;
-    S360_CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prioMode == 1 ? hi : prioMode == 2 ? lo : 0));
-  }
+  S360_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   initContextTables(c.get());
   *out = c.release();
   S360_API_END
