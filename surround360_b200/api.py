@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("S360_LIB", os.path.join(_HERE, "libs360b200.so"))  # S360_LIB: an alternative build of the same ABI
+LIB_PATH = os.path.join(_HERE, "libs360b200.so")
 
 
 class VrCamException(RuntimeError):
