@@ -100,6 +100,23 @@ int s360_ctx_set_graphs(s360_ctx* ctx, int on);
  * s360_ctx_reset_temporal renders like NONE. */
 int s360_ctx_set_temporal(s360_ctx* ctx, int on);
 int s360_ctx_reset_temporal(s360_ctx* ctx);
+/* Video mode through files, as the reference hands a frame's state to the next process (TRSP:200-255, 413-452):
+ * with temporal mode on, s360_frame_prepare builds the frame plan for (params, image size) without rendering, so that
+ * s360_temporal_sizes can report the sizes of the per-pair overlap images / side flows (overlap_w x overlap_h) and of the
+ * per-pole-slot extended images / pole flows (ext_w x ext_h). s360_temporal_import_side loads what the reference reads
+ * from flow/<prev>/flowLtoR_<pair>.bin, flowRtoL_<pair>.bin and debug/<prev>/flow_images/overlap_<pair>_{L,R}.png
+ * (BGRA8); s360_temporal_import_pole what it reads from flow/<prev>/flow_<slot>.bin and
+ * extendedFisheyeSpherical_<slot>.png (slot 0..3 = top_left, top_right, bottom_left, bottom_right; the extended side
+ * image of the previous frame is read by the reference but not used by PixFlow, PixFlow.h:101-118).
+ * s360_temporal_commit marks the imported state as "the previous frame" of the next s360_render_frame.
+ * The matching exports are the s360_frame_intermediate names "flowLtoR", "flowRtoL", "overlapL", "overlapR" (idx = pair)
+ * and "poleFlow", "extSide", "extFish" (idx = slot). */
+int s360_frame_prepare(s360_ctx* ctx, const s360_params* p, int img_w, int img_h);
+int s360_temporal_sizes(s360_ctx* ctx, int* overlap_w, int* overlap_h, int* ext_w, int* ext_h);
+int s360_temporal_import_side(s360_ctx* ctx, int pair, const float* flow_l_to_r, const float* flow_r_to_l, const uint8_t* overlap_l_bgra,
+                              const uint8_t* overlap_r_bgra);
+int s360_temporal_import_pole(s360_ctx* ctx, int slot, const float* flow, const uint8_t* ext_fisheye_bgra);
+int s360_temporal_commit(s360_ctx* ctx);
 int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, double* level_pixels, double* steps);
 
 /* ---- rig (RIG_JSON.md format) ---- */

@@ -288,6 +288,27 @@ class Context:
     def reset_temporal(self):
         _check(lib().s360_ctx_reset_temporal(self.h))
 
+    # video mode through files (TRSP:200-255, 413-452): previous-frame state from host buffers
+    def frame_prepare(self, params, img_w, img_h):
+        _check(lib().s360_frame_prepare(self.h, C.byref(params), int(img_w), int(img_h)))
+
+    def temporal_sizes(self):
+        v = [C.c_int() for _ in range(4)]
+        _check(lib().s360_temporal_sizes(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)   # overlap_w, overlap_h, ext_w, ext_h
+
+    def temporal_import_side(self, pair, flowLtoR, flowRtoL, overlapL, overlapR):
+        a, b = _c(flowLtoR, np.float32), _c(flowRtoL, np.float32)
+        l, r = _c(overlapL, np.uint8), _c(overlapR, np.uint8)
+        _check(lib().s360_temporal_import_side(self.h, int(pair), _p(a), _p(b), _p(l), _p(r)))
+
+    def temporal_import_pole(self, slot, flow, extFisheye):
+        a, x = _c(flow, np.float32), _c(extFisheye, np.uint8)
+        _check(lib().s360_temporal_import_pole(self.h, int(slot), _p(a), _p(x)))
+
+    def temporal_commit(self):
+        _check(lib().s360_temporal_commit(self.h))
+
     def set_graphs(self, on=True):
         _check(lib().s360_ctx_set_graphs(self.h, int(on)))
 

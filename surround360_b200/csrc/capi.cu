@@ -90,6 +90,40 @@ int s360_ctx_reset_temporal(s360_ctx* c) {
   resetTemporal(c);
   S360_API_END
 }
+int s360_frame_prepare(s360_ctx* c, const s360_params* p, int w, int h) {
+  S360_API_BEGIN
+  require(c != nullptr && p != nullptr, "null argument");
+  require(w > 0 && h > 0, "bad image size");
+  useDevice(c);
+  prepareFrame(c, *p, w, h);
+  S360_API_END
+}
+int s360_temporal_sizes(s360_ctx* c, int* ow, int* oh, int* ew, int* eh) {
+  S360_API_BEGIN
+  require(c != nullptr && ow && oh && ew && eh, "null argument");
+  temporalSizes(c, ow, oh, ew, eh);
+  S360_API_END
+}
+int s360_temporal_import_side(s360_ctx* c, int pair, const float* flr, const float* frl, const uint8_t* ol, const uint8_t* orr) {
+  S360_API_BEGIN
+  require(c != nullptr && flr && frl && ol && orr, "null argument");
+  useDevice(c);
+  temporalImportSide(c, pair, flr, frl, ol, orr);
+  S360_API_END
+}
+int s360_temporal_import_pole(s360_ctx* c, int slot, const float* flow, const uint8_t* extFish) {
+  S360_API_BEGIN
+  require(c != nullptr && flow && extFish, "null argument");
+  useDevice(c);
+  temporalImportPole(c, slot, flow, extFish);
+  S360_API_END
+}
+int s360_temporal_commit(s360_ctx* c) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  temporalCommit(c);
+  S360_API_END
+}
 int s360_ctx_set_graphs(s360_ctx* c, int on) {
   S360_API_BEGIN
   require(c != nullptr, "null context");

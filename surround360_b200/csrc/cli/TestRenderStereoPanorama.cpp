@@ -1,7 +1,8 @@
 // TestRenderStereoPanorama — command-line drop-in for the reference binary of the same name
 // (surround360_render/source/test/TestRenderStereoPanorama.cpp): same flags and defaults
 // (TRSP:44-70), same input layout <imgs_dir>/<camId>/<frame_number>.<ext>, same outputs
-// (stereo equirect PNG, optional cubemap PNG, flow .bin files). The render runs on the GPU through
+// (stereo equirect PNG, optional cubemap PNG, flow .bin files and the flow input PNGs the next frame's temporal
+// regularisation reads; --prev_frame_data_dir <previous frame number> as in TRSP:210-235, 418-436). The render runs on the GPU through
 // the C ABI (include/s360.h); this file only does flag parsing and file I/O.
 #include <dirent.h>
 #include <sys/stat.h>
@@ -89,16 +90,39 @@ void saveIntermediateFlow(s360_ctx* ctx, const char* name, int idx, const std::s
   check(s360_flow_save(path.c_str(), buf.data(), w, h));
 }
 
+void saveIntermediateImage(s360_ctx* ctx, const char* name, int idx, const std::string& path) {
+  int w, h, c, f;
+  check(s360_frame_intermediate(ctx, name, idx, nullptr, &w, &h, &c, &f));
+  std::vector<uint8_t> buf((size_t)w * h * 4);
+  check(s360_frame_intermediate(ctx, name, idx, buf.data(), &w, &h, &c, &f));
+  pngio::write(path, buf.data(), w, h, 4);
+}
+
+struct LoadedFlow {
+  float* p = nullptr;
+  ~LoadedFlow() { s360_free(p); }
+};
+// readFlowFromFile + size check against what this frame's flow of the same slot will be
+void loadPrevFlow(const std::string& path, int w, int h, LoadedFlow& out) {
+  int fw = 0, fh = 0;
+  check(s360_flow_load(path.c_str(), &out.p, &fw, &fh));
+  if (fw != w || fh != h) throw VrCamException("previous frame's flow has a different size: " + path);
+}
+pngio::Image loadPrevImage(const std::string& path, int w, int h) {  // imreadExceptionOnFail(path, -1)
+  pngio::Image im;
+  try { im = pngio::readColor(path, true); }
+  catch (const std::exception& e) { throw VrCamException(std::string("failed to load image: ") + path + " (" + e.what() + ")"); }
+  if (im.w != w || im.h != h) throw VrCamException("previous frame's flow image has a different size: " + path);
+  return im;
+}
+const char* kPoleSlotNames[4] = {"top_left", "top_right", "bottom_left", "bottom_right"};  // eyeName, TRSP:389-391
+
 int run(int argc, char** argv) {
   Flags F;
   F.parse(argc, argv);
   for (const char* n : {"rig_json_file", "imgs_dir", "frame_number", "output_data_dir", "output_equirect_path"}) requireArg(F, n);  // TRSP:717-721
   const bool verbose = F.i("v") >= 1;
   const double startTime = nowSec();
-  if (F.s("prev_frame_data_dir") != "NONE")
-    throw VrCamException("prev_frame_data_dir != NONE: temporal regularisation is available per flow (s360_flow_compute) but the frame "
-                         "pipeline of this build renders frames independently");
-
   s360_ctx* ctx = nullptr;
   check(s360_ctx_create(F.i("device"), &ctx));
   check(s360_rig_load_file(ctx, F.s("rig_json_file").c_str()));
@@ -159,6 +183,32 @@ int run(int argc, char** argv) {
   int ew, eh, cw, ch;
   check(s360_frame_output_size(ctx, &P, &ew, &eh, &cw, &ch));
   std::vector<uint8_t> eq((size_t)ew * eh * 3), cube((size_t)std::max(cw, 1) * std::max(ch, 1) * 3);
+  const std::string outDir = F.s("output_data_dir"), prev = F.s("prev_frame_data_dir");
+  if (prev != "NONE") {  // TRSP:210-235, 418-436: flow fields and flow input images of the previous frame
+    if (verbose) std::cerr << "Reading previous frame flow and images from: " << prev << "\n";
+    check(s360_ctx_set_temporal(ctx, 1));
+    check(s360_frame_prepare(ctx, &P, iw, ih));
+    int ow, oh, xw, xh;
+    check(s360_temporal_sizes(ctx, &ow, &oh, &xw, &xh));
+    const std::string flowPrevDir = outDir + "/flow/" + prev, imgPrevDir = outDir + "/debug/" + prev + "/flow_images";
+    for (int i = 0; i < nSide; ++i) {
+      LoadedFlow lr, rl;
+      loadPrevFlow(flowPrevDir + "/flowLtoR_" + std::to_string(i) + ".bin", ow, oh, lr);
+      loadPrevFlow(flowPrevDir + "/flowRtoL_" + std::to_string(i) + ".bin", ow, oh, rl);
+      const pngio::Image oL = loadPrevImage(imgPrevDir + "/overlap_" + std::to_string(i) + "_L.png", ow, oh);
+      const pngio::Image oR = loadPrevImage(imgPrevDir + "/overlap_" + std::to_string(i) + "_R.png", ow, oh);
+      check(s360_temporal_import_side(ctx, i, lr.p, rl.p, oL.data.data(), oR.data.data()));
+    }
+    for (int k = 0; k < 4; ++k) {
+      if (!((k < 2 && P.enable_top) || (k >= 2 && P.enable_bottom))) continue;
+      LoadedFlow fl;
+      loadPrevFlow(flowPrevDir + "/flow_" + kPoleSlotNames[k] + ".bin", xw, xh, fl);
+      const pngio::Image xf = loadPrevImage(imgPrevDir + "/extendedFisheyeSpherical_" + kPoleSlotNames[k] + ".png", xw, xh);
+      check(s360_temporal_import_pole(ctx, k, fl.p, xf.data.data()));
+    }
+    check(s360_temporal_commit(ctx));
+    if (verbose) std::cerr << "Loaded previous frame's flow OK\n";
+  }
   check(s360_ctx_set_graphs(ctx, 0));  // single frame: plain launches, so the per-stage timers are filled
   check(s360_render_frame(ctx, &P, ptrs.data(), iw, ih, eq.data(), cw ? cube.data() : nullptr));
   float ms[7];
@@ -168,16 +218,29 @@ int run(int argc, char** argv) {
   pngio::write(F.s("output_equirect_path"), eq.data(), ew, eh, 3);
   if (cw) pngio::write(F.s("output_cubemap_path"), cube.data(), cw, ch, 3);
   if (F.b("save_flow_data")) {  // TRSP:246-255, 450-452: what the next frame's temporal regularisation reads
-    const std::string flowDir = F.s("output_data_dir") + "/flow/" + frame;
+    const std::string flowDir = outDir + "/flow/" + frame, flowImagesDir = outDir + "/debug/" + frame + "/flow_images";
     struct stat st;
+    if (stat(flowImagesDir.c_str(), &st) == 0) {  // TRSP:203-208, 413-415: "we will need them in the next frame"
+      for (int i = 0; i < nSide; ++i) {
+        saveIntermediateImage(ctx, "overlapL", i, flowImagesDir + "/overlap_" + std::to_string(i) + "_L.png");
+        saveIntermediateImage(ctx, "overlapR", i, flowImagesDir + "/overlap_" + std::to_string(i) + "_R.png");
+      }
+      for (int k = 0; k < 4; ++k)
+        if ((k < 2 && P.enable_top) || (k >= 2 && P.enable_bottom)) {
+          saveIntermediateImage(ctx, "extSide", k, flowImagesDir + "/extendedSideSpherical_" + kPoleSlotNames[k] + ".png");
+          saveIntermediateImage(ctx, "extFish", k, flowImagesDir + "/extendedFisheyeSpherical_" + kPoleSlotNames[k] + ".png");
+        }
+    } else if (verbose) {
+      std::cerr << "flow image directory " << flowImagesDir << " does not exist; flow input images not saved\n";
+    }
     if (stat(flowDir.c_str(), &st) == 0) {  // directories are created by the driver script (batch_process_video.py:116-118)
       for (int i = 0; i < nSide; ++i) {
         saveIntermediateFlow(ctx, "flowLtoR", i, flowDir + "/flowLtoR_" + std::to_string(i) + ".bin");
         saveIntermediateFlow(ctx, "flowRtoL", i, flowDir + "/flowRtoL_" + std::to_string(i) + ".bin");
       }
-      const char* names[4] = {"top_left", "top_right", "bottom_left", "bottom_right"};
       for (int k = 0; k < 4; ++k)
-        if ((k < 2 && P.enable_top) || (k >= 2 && P.enable_bottom)) saveIntermediateFlow(ctx, "poleFlow", k, flowDir + "/flow_" + names[k] + ".bin");
+        if ((k < 2 && P.enable_top) || (k >= 2 && P.enable_bottom))
+          saveIntermediateFlow(ctx, "poleFlow", k, flowDir + "/flow_" + kPoleSlotNames[k] + ".bin");
     } else if (verbose) {
       std::cerr << "flow directory " << flowDir << " does not exist; flow data not saved\n";
     }

@@ -37,8 +37,8 @@ inline int paeth(int a, int b, int c) {
   return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
-// -> BGR8
-inline Image readColor(const std::string& path) {
+// -> BGR8 (cv::imread CV_LOAD_IMAGE_COLOR), or with keepAlpha -> BGRA8 (cv::imread flag -1 on an 8-bit RGBA file; alpha 255 when the file has none)
+inline Image readColor(const std::string& path, bool keepAlpha = false) {
   std::vector<uint8_t> buf = readFile(path);
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   if (buf.size() < 8 || std::memcmp(buf.data(), sig, 8)) throw std::runtime_error("not a PNG file (only PNG input is supported by this tool): " + path);
@@ -70,8 +70,9 @@ inline Image readColor(const std::string& path) {
     throw std::runtime_error("PNG inflate failed: " + path);
   std::vector<uint8_t> prev(stride, 0), cur(stride);
   Image img;
-  img.w = w; img.h = h; img.channels = 3;
-  img.data.resize((size_t)w * h * 3);
+  const int oc = keepAlpha ? 4 : 3;
+  img.w = w; img.h = h; img.channels = oc;
+  img.data.resize((size_t)w * h * oc);
   for (int y = 0; y < h; ++y) {
     const uint8_t* in = &raw[(stride + 1) * (size_t)y];
     const int ft = in[0];
@@ -89,14 +90,15 @@ inline Image readColor(const std::string& path) {
       }
       cur[i] = (uint8_t)v;
     }
-    uint8_t* out = &img.data[(size_t)y * w * 3];
+    uint8_t* out = &img.data[(size_t)y * w * oc];
     for (int x = 0; x < w; ++x) {
       const uint8_t* p = &cur[(size_t)x * bpp];
       uint8_t r, g, b;
       if (ctype == 0 || ctype == 4) r = g = b = p[0];                // high byte first for 16-bit
       else if (ctype == 3) { const size_t k = (size_t)p[0] * 3; if (k + 2 >= palette.size()) throw std::runtime_error("bad palette index: " + path); r = palette[k]; g = palette[k + 1]; b = palette[k + 2]; }
       else { r = p[0]; g = p[bps]; b = p[2 * bps]; }
-      out[x * 3] = b; out[x * 3 + 1] = g; out[x * 3 + 2] = r;
+      out[x * oc] = b; out[x * oc + 1] = g; out[x * oc + 2] = r;
+      if (keepAlpha) out[x * oc + 3] = ctype == 6 ? p[3 * bps] : ctype == 4 ? p[bps] : 255;
     }
     std::swap(prev, cur);
   }

@@ -642,6 +642,19 @@ int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w,
         copy2d(F.poleWarped.as<uchar4>() + (size_t)k * eqW * g.poleH, (size_t)eqW * 4, g.poleH, (size_t)eqW * 4);
       }
     }
+  } else if (n == "overlapL" || n == "overlapR") {
+    // the flow inputs of pair idx (TRSP:196-198): right overlapW columns of projection idx, left overlapW columns of idx+1
+    if (idx < 0 || idx >= F.numCams) throw std::runtime_error("pair index out of range");
+    *w = g.overlapW; *h = g.camH; *ch = 4; *isFloat = 0;
+    const uchar4* src = n == "overlapL" ? F.proj.as<uchar4>() + (size_t)idx * g.camW * g.camH + (g.camW - g.overlapW)
+                                         : F.proj.as<uchar4>() + (size_t)((idx + 1) % F.numCams) * g.camW * g.camH;
+    copy2d(src, (size_t)g.overlapW * 4, g.camH, (size_t)g.camW * 4);
+  } else if (n == "extSide" || n == "extFish") {
+    int k = idx;   // reference order: top_left, top_right, bottom_left, bottom_right
+    if (!F.top) k -= 2;
+    if (k < 0 || k >= F.nPole) throw std::runtime_error("pole slot not rendered");
+    *w = g.extW; *h = g.poleH; *ch = 4; *isFloat = 0;
+    copy2d((n == "extSide" ? F.extSide : F.extFish).as<uchar4>() + (size_t)k * g.extW * g.poleH, (size_t)g.extW * 4, g.poleH, (size_t)g.extW * 4);
   } else if (n == "eyeL" || n == "eyeR") {
     const int e = n == "eyeL" ? 0 : 1;
     if (!F.eyePre[e].p) throw std::runtime_error("enable keep_intermediates before rendering");
@@ -652,6 +665,55 @@ int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w,
   }
   return 0;
 }
+
+// ------------------------------------------------------------------------------------
+// video mode through files (TRSP:200-255, 413-452): the previous frame's state arrives from the host
+// ------------------------------------------------------------------------------------
+void prepareFrame(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
+  if (!planMatches(c, P, imgW, imgH)) buildPlan(c, P, imgW, imgH);
+}
+static FramePlan& temporalPlan(s360_ctx* c) {
+  if (!c->plan) throw std::runtime_error("no frame plan: call s360_frame_prepare (or render a frame) first");
+  if (!c->plan->temporal) throw std::runtime_error("temporal mode is off: call s360_ctx_set_temporal before s360_frame_prepare");
+  return *c->plan;
+}
+void temporalSizes(s360_ctx* c, int* overlapW, int* overlapH, int* extW, int* extH) {
+  if (!c->plan) throw std::runtime_error("no frame plan: call s360_frame_prepare (or render a frame) first");
+  const Geometry& g = c->plan->g;
+  *overlapW = g.overlapW; *overlapH = g.camH;
+  *extW = c->plan->nPole ? g.extW : 0; *extH = c->plan->nPole ? g.poleH : 0;
+}
+void temporalImportSide(s360_ctx* c, int pair, const float* flowLtoR, const float* flowRtoL, const uint8_t* overlapL, const uint8_t* overlapR) {
+  FramePlan& F = temporalPlan(c);
+  const Geometry& g = F.g;
+  if (pair < 0 || pair >= F.numCams) throw std::runtime_error("pair index out of range");
+  cudaStream_t st = c->stream;
+  const size_t per = (size_t)g.overlapW * g.camH;
+  float2* pf = F.prevFlowSide.as<float2>();   // [2][numCams]: LtoR then RtoL, like flowSide
+  S360_CUDA_CHECK(cudaMemcpyAsync(pf + (size_t)pair * per, flowLtoR, per * 8, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(pf + (size_t)(F.numCams + pair) * per, flowRtoL, per * 8, cudaMemcpyHostToDevice, st));
+  // the overlap images are views into the projections (enqueueFrame): L = right columns of `pair`, R = left columns of pair+1
+  uchar4* pp = F.prevProj.as<uchar4>();
+  const size_t rowB = (size_t)g.overlapW * 4, pitchB = (size_t)g.camW * 4;
+  S360_CUDA_CHECK(cudaMemcpy2DAsync(pp + (size_t)pair * g.camW * g.camH + (g.camW - g.overlapW), pitchB, overlapL, rowB, rowB, g.camH,
+                                    cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpy2DAsync(pp + (size_t)((pair + 1) % F.numCams) * g.camW * g.camH, pitchB, overlapR, rowB, rowB, g.camH,
+                                    cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));   // the caller may release its buffers on return
+}
+void temporalImportPole(s360_ctx* c, int slot, const float* flow, const uint8_t* extFish) {
+  FramePlan& F = temporalPlan(c);
+  const Geometry& g = F.g;
+  int k = slot;   // reference order: top_left, top_right, bottom_left, bottom_right
+  if (!F.top) k -= 2;
+  if (slot < 0 || slot > 3 || k < 0 || k >= F.nPole) throw std::runtime_error("pole slot not rendered");
+  cudaStream_t st = c->stream;
+  const size_t extPx = (size_t)g.extW * g.poleH;
+  S360_CUDA_CHECK(cudaMemcpyAsync(F.prevPoleFlow.as<float2>() + (size_t)k * extPx, flow, extPx * 8, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(F.prevExtFish.as<uchar4>() + (size_t)k * extPx, extFish, extPx * 4, cudaMemcpyHostToDevice, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+void temporalCommit(s360_ctx* c) { temporalPlan(c).prevValid = true; }
 
 // ------------------------------------------------------------------------------------
 // poleToSideFlowThread as a stand-alone operator (C-ABI)

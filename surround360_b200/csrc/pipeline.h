@@ -71,6 +71,12 @@ void renderFrameDevice(s360_ctx* c, const s360_params& p, const uint8_t* const* 
 void renderFrameHost(s360_ctx* c, const s360_params& p, const uint8_t* const* images, int imgW, int imgH, uint8_t* equirect,
                      uint8_t* cubemap);
 int frameIntermediate(s360_ctx* c, const char* name, int idx, void* out, int* w, int* h, int* ch, int* isFloat);
+// video mode through files (TRSP:200-255, 413-452): plan without rendering, previous-frame state from host buffers
+void prepareFrame(s360_ctx* c, const s360_params& p, int imgW, int imgH);
+void temporalSizes(s360_ctx* c, int* overlapW, int* overlapH, int* extW, int* extH);
+void temporalImportSide(s360_ctx* c, int pair, const float* flowLtoR, const float* flowRtoL, const uint8_t* overlapL, const uint8_t* overlapR);
+void temporalImportPole(s360_ctx* c, int slot, const float* flow, const uint8_t* extFish);
+void temporalCommit(s360_ctx* c);
 void poleToSide(s360_ctx* c, const s360_params& p, const uint8_t* sideHost, int sw, int sh, const uint8_t* fishHost, int fw, int fh,
                 uint8_t* warpedOut, float* flowOut);
 std::vector<int> gaussKernelFixed8(int n, double sigma);

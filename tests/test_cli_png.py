@@ -68,3 +68,28 @@ def test_cli_flag_surface():
     # glog flags the driver script passes are accepted (scripts/batch_process_video.py:31-34)
     r = run_cli("--logbuflevel", "-1", "--stderrthreshold", "0", "--v", "1", "--log_dir", "/tmp")
     assert "missing required command line argument: rig_json_file" in r.stderr
+
+
+def test_png_bgra_roundtrip_matches_cv2_unchanged(tool):
+    """overlap_<i>_{L,R}.png / extended*Spherical_*.png hand-over (TRSP:203-208, 413-415): written as 4-channel PNG,
+    read back with cv::imread(..., -1)."""
+    exe, d = tool
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (29, 41, 4)).astype(np.uint8)
+    raw = str(d / "in4.raw")
+    with open(raw, "wb") as f:
+        f.write(np.array([41, 29, 4], np.int32).tobytes())
+        f.write(img.tobytes())
+    png = str(d / "bgra.png")
+    subprocess.check_call([exe, "write", raw, png])
+    assert np.array_equal(cv2.imread(png, cv2.IMREAD_UNCHANGED), img)       # our writer, OpenCV's reader
+    out = str(d / "out4.raw")
+    subprocess.check_call([exe, "read4", png, out])
+    b = open(out, "rb").read()
+    w, h = np.frombuffer(b[:8], np.int32)
+    assert np.array_equal(np.frombuffer(b[8:], np.uint8).reshape(h, w, 4), img)
+    png2 = str(d / "cv_bgra.png")
+    assert cv2.imwrite(png2, img)                                            # OpenCV's writer, our reader
+    subprocess.check_call([exe, "read4", png2, out])
+    b = open(out, "rb").read()
+    assert np.array_equal(np.frombuffer(b[8:], np.uint8).reshape(29, 41, 4), img)

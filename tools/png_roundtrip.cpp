@@ -1,12 +1,12 @@
-// Test helper for csrc/cli/png_io.h:  png_roundtrip read <in.png> <out.raw>   (BGR8 dump: int32 w, int32 h, bytes)
+// Test helper for csrc/cli/png_io.h:  png_roundtrip read|read4 <in.png> <out.raw>   (BGR8 / BGRA8 dump: int32 w, int32 h, bytes)
 //                                     png_roundtrip write <in.raw> <out.png>  (raw = int32 w, h, channels, bytes)
 #include <cstdio>
 #include "../surround360_b200/csrc/cli/png_io.h"
 int main(int argc, char** argv) {
   if (argc != 4) return 2;
   try {
-    if (std::string(argv[1]) == "read") {
-      pngio::Image im = pngio::readColor(argv[2]);
+    if (std::string(argv[1]) == "read" || std::string(argv[1]) == "read4") {
+      pngio::Image im = pngio::readColor(argv[2], std::string(argv[1]) == "read4");
       FILE* f = fopen(argv[3], "wb");
       int32_t hdr[2] = {im.w, im.h};
       fwrite(hdr, 4, 2, f); fwrite(im.data.data(), 1, im.data.size(), f); fclose(f);
