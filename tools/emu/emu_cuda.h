@@ -1,0 +1,98 @@
+// tools/emu: a minimal CPU execution model for this repository's CUDA kernels -- DEVELOPMENT TOOL ONLY.
+// It lets the exact kernel source (rewritten by emu_prep.py: launches and inline PTX only) run on host
+// threads so that a change can be checked bit-for-bit against the oracle before GPU time is spent on it.
+// Nothing in the package, the C ABI, the tests or bench.py loads it; the product has no CPU path.
+//
+// Model: a launch runs synchronously. Kernels without barriers run their threads one after another;
+// kernels with __syncthreads run one block at a time on real threads with a barrier; kernels with warp
+// shuffles / inter-block spin-waits (k_sweep) run every warp of the grid on real threads, lanes in
+// lock-step at the shuffles. __shared__ becomes a static array (one block at a time => shared by the block).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __CUDACC__ 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct uchar4 { unsigned char x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+static inline float2 make_float2(float x, float y) { return {x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return {x, y, z, w}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
+
+extern thread_local uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
+
+// ---- device intrinsics ----
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline int __float2int_rn(float v) { return (int)std::nearbyintf(v); }   // default rounding mode: to nearest even
+static inline int __float2int_rd(float v) { return (int)std::floor(v); }
+static inline int __float2int_rz(float v) { return (int)v; }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline unsigned __vminu2(unsigned a, unsigned b) {
+  return std::min(a & 0xffffu, b & 0xffffu) | (std::min(a >> 16, b >> 16) << 16);
+}
+using std::max;
+using std::min;
+static inline int min(int a, unsigned b) { return (int)std::min<long long>(a, b); }
+static inline unsigned min(unsigned a, int b) { return (unsigned)std::min<long long>(a, b); }
+
+namespace emu {
+void syncthreads();
+float shfl_up(float v, unsigned delta);
+int shfl_idx(int v, int lane);
+float2 ld_volatile(const float2* p);
+void st_volatile(float2* p, float2 v);
+enum Mode { SEQUENTIAL, BLOCK_BARRIER, GRID_WARPS };
+void launch(const char* name, dim3 grid, dim3 block, Mode mode, const std::function<void()>& body);
+}  // namespace emu
+static inline void __syncthreads() { emu::syncthreads(); }
+static inline float __shfl_up_sync(unsigned, float v, unsigned d) { return emu::shfl_up(v, d); }
+static inline int __shfl_sync(unsigned, int v, int lane) { return emu::shfl_idx(v, lane); }
+
+// ---- runtime API subset (device memory is host memory) ----
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum cudaError_t { cudaSuccess = 0, cudaErrorUnknown = 999 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulator"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorUnknown; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
