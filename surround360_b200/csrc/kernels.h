@@ -176,6 +176,7 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   uchar4* small1_ = nullptr;
   float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *g1Scratch_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
+  int* sweepBad_ = nullptr;
   void* arena_ = nullptr;
   void* boundaryAlloc_ = nullptr;
   bool bound_ = false;

@@ -59,6 +59,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b
 static inline unsigned __vminu2(unsigned a, unsigned b) {
   return std::min(a & 0xffffu, b & 0xffffu) | (std::min(a >> 16, b >> 16) << 16);
 }
+static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 using std::max;
 using std::min;
 static inline int min(int a, unsigned b) { return (int)std::min<long long>(a, b); }
