@@ -174,14 +174,14 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   std::vector<float*> D_, motionPyr_;
   uchar4* small0_ = nullptr;
   uchar4* small1_ = nullptr;
-  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *g1Scratch_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
+  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
   int* sweepBad_ = nullptr;
   void* arena_ = nullptr;
   void* boundaryAlloc_ = nullptr;
   bool bound_ = false;
   std::vector<size_t> oI0_, oI1_, oA0_, oA1_, oPrev_, oMot_, oDump_;
-  size_t oS0_ = 0, oS1_ = 0, oRec_ = 0, oQuad_ = 0, oD_ = 0, oFA_ = 0, oFull_ = 0, oFB_ = 0, oG1_ = 0, oTmp_ = 0;
+  size_t oS0_ = 0, oS1_ = 0, oRec_ = 0, oQuad_ = 0, oD_ = 0, oFA_ = 0, oFull_ = 0, oFB_ = 0, oTmp_ = 0;
 };
 
 }  // namespace s360
