@@ -149,7 +149,7 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   int levelW(int l) const { return lw_[l]; }
   int levelH(int l) const { return lh_[l]; }
   // sweep-kernel profiling: CUDA events around every k_sweep launch (on the launching stream)
-  struct SweepProfile { double ms = 0, levelPixels = 0, steps = 0; unsigned long long launches = 0; };
+  struct SweepProfile { double ms = 0, levelPixels = 0, steps = 0; unsigned long long launches = 0, fallbacks = 0; };
   void enableProfile(bool on) { profile_ = on; }
   // call after the stream has been synchronised; accumulates and clears pending events
   void collectProfile(SweepProfile* acc);
