@@ -52,6 +52,8 @@ extern thread_local dim3 blockDim, gridDim;
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline int __float2int_rn(float v) { return (int)std::nearbyintf(v); }   // default rounding mode: to nearest even
 static inline int __float2int_rd(float v) { return (int)std::floor(v); }
 static inline int __float2int_rz(float v) { return (int)v; }
@@ -93,6 +95,28 @@ static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcp
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+struct cudaDeviceProp { char name[256]; int multiProcessorCount; size_t totalGlobalMem; int major, minor; };
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { std::memset(p, 0, sizeof(*p)); std::strcpy(p->name, "host emulation"); p->multiProcessorCount = 148; p->major = 10; return cudaSuccess; }
+enum { cudaStreamNonBlocking = 1 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t wbytes, size_t rows, cudaMemcpyKind, cudaStream_t = nullptr) {
+  for (size_t r = 0; r < rows; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, wbytes);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t wbytes, size_t rows, cudaMemcpyKind k) { return cudaMemcpy2DAsync(d, dp, s, sp, wbytes, rows, k); }
+// CUDA graphs are not modelled: the emulated context renders with plain launches (s360_ctx_set_graphs(ctx, 0))
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal };
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorUnknown; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*) { return cudaErrorUnknown; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorUnknown; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorUnknown; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
