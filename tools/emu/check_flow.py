@@ -20,11 +20,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def build(src=None):
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    gen = os.path.join(HERE, "build", "flow_kernels_emu.cpp")
+    bdir = os.environ.get("EMU_BUILD", os.path.join(HERE, "build"))
+    os.makedirs(bdir, exist_ok=True)
+    gen = os.path.join(bdir, "flow_kernels_emu.cpp")
     subprocess.check_call([sys.executable, os.path.join(HERE, "emu_prep.py"), src or os.path.join(ROOT, "surround360_b200", "csrc", "flow_kernels.cu"), gen],
                           stdout=subprocess.DEVNULL)
-    so = os.path.join(HERE, "build", "libemu_flow.so")
+    so = os.path.join(bdir, "libemu_flow.so")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(HERE, "stub"),
                            "-I", os.path.join(ROOT, "surround360_b200", "csrc"), "-o", so, os.path.join(HERE, "emu_rt.cpp"),
                            os.path.join(HERE, "emu_flow.cpp"), gen])

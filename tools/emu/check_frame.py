@@ -74,6 +74,36 @@ def main():
     print("frame 1 from imported state vs in-process chain:", "bit-exact" if ok2 else "MISMATCH")
     ok3 = not np.array_equal(chained, eq0)
     b.close()
+    if "--cli" in sys.argv:   # the command-line tool linked against the emulated library: two processes, files in between
+        import json
+        import subprocess
+        import tempfile
+        import cv2
+        exe = os.path.join(run_tests.BUILD, "TestRenderStereoPanorama_emu")
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "surround360_b200", "csrc", "cli", "TestRenderStereoPanorama.cpp"),
+                               "-L", run_tests.BUILD, "-ls360b200_emu", "-lz", "-pthread", "-Wl,-rpath," + run_tests.BUILD])
+        tmp = tempfile.mkdtemp(prefix="s360emu")
+        rig = json.load(open(RIG17))
+        imgs, out = os.path.join(tmp, "rgb"), os.path.join(tmp, "out")
+        for name, fr in (("000000", f0), ("000001", f1)):
+            for cam, im in zip(rig["cameras"], fr):
+                os.makedirs(os.path.join(imgs, cam["id"]), exist_ok=True)
+                assert cv2.imwrite(os.path.join(imgs, cam["id"], name + ".png"), im)
+            os.makedirs(os.path.join(out, "flow", name))
+            os.makedirs(os.path.join(out, "debug", name, "flow_images"))
+        for frame, prev in (("000000", "NONE"), ("000001", "000000")):
+            cmd = [exe, "--rig_json_file", RIG17, "--imgs_dir", imgs, "--frame_number", frame, "--output_data_dir", out, "--prev_frame_data_dir", prev,
+                   "--output_equirect_path", os.path.join(out, f"eqr_{frame}.png"), "--enable_top", "--enable_bottom", "--sharpening", "0.25",
+                   "--eqr_width", "700", "--eqr_height", "350", "--final_eqr_width", "512", "--final_eqr_height", "512"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+        ok4 = np.array_equal(cv2.imread(os.path.join(out, "eqr_000000.png"), cv2.IMREAD_COLOR), eq0)
+        ok5 = np.array_equal(cv2.imread(os.path.join(out, "eqr_000001.png"), cv2.IMREAD_COLOR), chained)
+        ok6 = np.array_equal(cv2.imread(os.path.join(out, "debug", "000000", "flow_images", "overlap_3_L.png"), cv2.IMREAD_UNCHANGED), side[3][2])
+        print("CLI frame 0 vs library:", "bit-exact" if ok4 else "MISMATCH")
+        print("CLI frame 1 with --prev_frame_data_dir 000000 vs in-process chain:", "bit-exact" if ok5 else "MISMATCH")
+        print("CLI overlap_3_L.png vs intermediate:", "bit-exact" if ok6 else "MISMATCH")
+        ok = ok and ok4 and ok5 and ok6
     sys.exit(0 if (ok and ok1 and ok2 and ok3) else 1)
 
 

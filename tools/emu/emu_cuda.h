@@ -3,14 +3,13 @@
 // threads so that a change can be checked bit-for-bit against the oracle before GPU time is spent on it.
 // Nothing in the package, the C ABI, the tests or bench.py loads it; the product has no CPU path.
 //
-// Model: a launch runs synchronously. Kernels without barriers run their threads one after another;
-// kernels with __syncthreads run one block at a time on real threads with a barrier; kernels with warp
-// shuffles / inter-block spin-waits (k_sweep) run every warp of the grid on real threads, lanes in
-// lock-step at the shuffles. __shared__ becomes a static array (one block at a time => shared by the block).
+// Model: a launch runs synchronously. Kernels without barriers run their threads one after another; CUDA threads of the
+// other kernels are fibers: a block with __syncthreads runs round-robin on one OS thread and switches at the barrier;
+// kernels with warp shuffles / inter-block spin-waits (k_sweep*) get one OS thread per warp whose 32 lane-fibers advance
+// in lock-step at the shuffles, every warp of the grid resident. __shared__ becomes a static array (one block at a time).
 #pragma once
 #include <algorithm>
 #include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "surround360_b200", "csrc")
-BUILD = os.path.join(HERE, "build")
+BUILD = os.environ.get("EMU_BUILD", os.path.join(HERE, "build"))
 
 
 def build():
