@@ -204,7 +204,7 @@ void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, in
   uint16_t* t = reinterpret_cast<uint16_t*>(scratch + 2 * plane);
   k_extract_alpha<<<grid2d(w, rows, b), b, 0, st>>>(src, w, srcH, rows, flip, a0);
   if (erodeSize == kErR) {
-    // a1 <- vertical minimum; the u16 scratch `t` (unused until the blur) holds the final eroded plane, copied back to a1's role
+    // the u16 scratch `t` (not needed before the blur) first holds the vertical minimum; a1 receives the eroded plane
     uint8_t* vtmp = reinterpret_cast<uint8_t*>(t);
     k_erode_v31<<<dim3(iDivUp(w, 128), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, w, rows, vtmp);
     k_erode_h31<<<dim3(iDivUp(w, kErTileW), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, vtmp, w, rows, a1);
