@@ -11,7 +11,7 @@ if [ "${1:-}" = "--build-variants" ]; then
   # A/B libraries: name=flags (the default build is k_sweep2, 96 registers, bands over the shorter side)
   mkdir -p build_variants /tmp/s360_variant
   rm -rf /tmp/s360_variant/csrc && cp -r surround360_b200/csrc /tmp/s360_variant/
-  for v in "sweep2_128regs=-DS360_SWEEP2_MINBLOCKS=4" "sweep1_fast=-DS360_SWEEP_KERNEL=1" "sweep_generic=-DS360_SWEEP_KERNEL=0" "rowbands=-DS360_SWEEP_TRANSPOSE=0" "median8=-DS360_MEDIAN_ROWS=8"; do
+  for v in "sweep2_128regs=-DS360_SWEEP2_MINBLOCKS=4" "sweep2_80regs=-DS360_SWEEP2_MINBLOCKS=6" "sweep1_fast=-DS360_SWEEP_KERNEL=1" "sweep_generic=-DS360_SWEEP_KERNEL=0" "rowbands=-DS360_SWEEP_TRANSPOSE=0" "median8=-DS360_MEDIAN_ROWS=8"; do
     name=${v%%=*}; flags=${v#*=}
     (cd /tmp/s360_variant/csrc && mkdir -p build &&
      nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -Xcompiler -fPIC $flags -c flow_kernels.cu -o build/flow_kernels_$name.o) || exit 1
