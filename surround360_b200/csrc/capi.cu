@@ -511,6 +511,7 @@ int s360_flow_load(const char* path, float** out, int* w, int* h) {
     throw std::runtime_error(std::string("bad flow file: ") + path);
   }
   float* buf = (float*)std::malloc((size_t)rows * cols * 8);
+  if (!buf) { std::fclose(f); throw std::runtime_error(std::string("out of memory reading flow file: ") + path); }
   const size_t got = std::fread(buf, 8, (size_t)rows * cols, f);
   std::fclose(f);
   if (got != (size_t)rows * cols) { std::free(buf); throw std::runtime_error(std::string("truncated flow file: ") + path); }
