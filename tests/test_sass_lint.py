@@ -22,3 +22,11 @@ def test_no_packed_fp32_contraction_and_sm100a_only():
     assert len(ops) > 10000
     packed = sorted({o for o in ops if o.split(".")[0] in ("FFMA2", "FADD2", "FMUL2")})
     assert not packed, f"packed FP32 instructions in the library: {packed}"
+    # fused multiply-adds may only come from the compiler's division / square-root / exp expansions (which start from a MUFU
+    # approximation) or from their written-out copies: a kernel without MUFU must not contain FFMA or DFMA at all
+    for f in re.split(r"\n\s*Function : ", out)[1:]:
+        name = f.split("\n", 1)[0].strip()
+        fops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", f, flags=re.M)
+        fma = sum(o.split(".")[0] in ("FFMA", "DFMA") for o in fops)
+        mufu = sum(o.startswith("MUFU") for o in fops)
+        assert fma == 0 or mufu > 0, f"{name}: {fma} fused multiply-adds without any division/sqrt expansion"
