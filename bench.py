@@ -282,7 +282,7 @@ def main():
         c.profile_enable(True)
     prof_steps = min(args.steps, 2)
     ms_prof, _, _ = timed_pass(prof_steps * F)
-    prof = dict(ms=0.0, launches=0, level_pixels=0.0, steps=0.0)
+    prof = dict(ms=0.0, launches=0, level_pixels=0.0, steps=0.0, fallbacks=0)
     for c in ctxs:
         pr = c.profile_sweep()
         for k in prof:
@@ -344,7 +344,7 @@ def main():
                 "peak_source": peak_src,
                 "avg_launch_ms": prof["ms"] / prof["launches"], "launches_timed": prof["launches"],
                 "ns_per_wavefront_step": 1e6 * prof["ms"] / max(prof["steps"], 1.0),
-                "sweep_ms_per_frame": prof["ms"] / (prof_steps * F), "instrumented_pass_ms_per_step": ms_prof / prof_steps,
+                "sweep_ms_per_frame": prof["ms"] / (prof_steps * F), "sweep_generic_reruns_last_frames": prof["fallbacks"], "instrumented_pass_ms_per_step": ms_prof / prof_steps,
                 "note": "dependency-latency-bound recurrence: reported against the HBM roofline for completeness"}
 
     cpu_baseline = None

@@ -118,6 +118,9 @@ int s360_temporal_import_side(s360_ctx* ctx, int pair, const float* flow_l_to_r,
 int s360_temporal_import_pole(s360_ctx* ctx, int slot, const float* flow, const uint8_t* ext_fisheye_bgra);
 int s360_temporal_commit(s360_ctx* ctx);
 int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, double* level_pixels, double* steps);
+/* sweep launches (since s360_profile_enable) that the generic kernel had to repeat because an operand left the range of the
+ * fast kernel's written-out div/sqrt sequences; valid after s360_profile_sweep */
+int s360_profile_sweep_fallbacks(s360_ctx* ctx, unsigned long long* fallbacks);
 
 /* ---- rig (RIG_JSON.md format) ---- */
 int s360_rig_load_file(s360_ctx* ctx, const char* json_path);

@@ -318,7 +318,9 @@ class Context:
     def profile_sweep(self):
         ms, n, px, steps = C.c_double(), C.c_ulonglong(), C.c_double(), C.c_double()
         _check(lib().s360_profile_sweep(self.h, C.byref(ms), C.byref(n), C.byref(px), C.byref(steps)))
-        return dict(ms=ms.value, launches=n.value, level_pixels=px.value, steps=steps.value)
+        fb = C.c_ulonglong()
+        _check(lib().s360_profile_sweep_fallbacks(self.h, C.byref(fb)))
+        return dict(ms=ms.value, launches=n.value, level_pixels=px.value, steps=steps.value, fallbacks=fb.value)
 
     def intermediate(self, name, idx=0):
         w, h, c, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -147,6 +147,12 @@ int s360_profile_sweep(s360_ctx* c, double* ms, unsigned long long* launches, do
   if (steps) *steps = c->sweepProfile.steps;
   S360_API_END
 }
+int s360_profile_sweep_fallbacks(s360_ctx* c, unsigned long long* fallbacks) {
+  S360_API_BEGIN
+  require(c != nullptr && fallbacks != nullptr, "null argument");
+  *fallbacks = c->sweepProfile.fallbacks;   // filled by the last s360_profile_sweep
+  S360_API_END
+}
 
 // ---- rig ----
 int s360_rig_load_json(s360_ctx* c, const char* text) {

@@ -149,7 +149,7 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   int levelW(int l) const { return lw_[l]; }
   int levelH(int l) const { return lh_[l]; }
   // sweep-kernel profiling: CUDA events around every k_sweep launch (on the launching stream)
-  struct SweepProfile { double ms = 0, levelPixels = 0, steps = 0; unsigned long long launches = 0; };
+  struct SweepProfile { double ms = 0, levelPixels = 0, steps = 0; unsigned long long launches = 0, fallbacks = 0; };
   void enableProfile(bool on) { profile_ = on; }
   // call after the stream has been synchronised; accumulates and clears pending events
   void collectProfile(SweepProfile* acc);
@@ -174,13 +174,14 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   std::vector<float*> D_, motionPyr_;
   uchar4* small0_ = nullptr;
   uchar4* small1_ = nullptr;
-  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *g1Scratch_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
+  float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
+  int* sweepBad_ = nullptr;
   void* arena_ = nullptr;
   void* boundaryAlloc_ = nullptr;
   bool bound_ = false;
   std::vector<size_t> oI0_, oI1_, oA0_, oA1_, oPrev_, oMot_, oDump_;
-  size_t oS0_ = 0, oS1_ = 0, oRec_ = 0, oQuad_ = 0, oD_ = 0, oFA_ = 0, oFull_ = 0, oFB_ = 0, oG1_ = 0, oTmp_ = 0;
+  size_t oS0_ = 0, oS1_ = 0, oRec_ = 0, oQuad_ = 0, oD_ = 0, oFA_ = 0, oFull_ = 0, oFB_ = 0, oTmp_ = 0;
 };
 
 }  // namespace s360

@@ -502,6 +502,8 @@ static void enqueueFrame(s360_ctx* c, const uint8_t* const* imagesDev, uint8_t* 
     else launchPackBGR(st, F.eye(e, (size_t)eqW * eqH), eqW, eqH, eqW, dst);
   }
   stageEvent(6);
+  // a rejected launch (bad configuration) does not stick to the stream: fail here instead of returning a stale frame
+  S360_CUDA_CHECK(cudaGetLastError());
 }
 
 // A frame is ~1000 small launches; replaying it as one CUDA graph removes the host launch cost and

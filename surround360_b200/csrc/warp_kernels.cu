@@ -273,11 +273,18 @@ template <int CN>
 __global__ void __launch_bounds__(256)
 k_resize_cubic8(const uchar4* __restrict__ src, int sw, int sh, int spitch, uchar4* __restrict__ dst, int dw, int dh, int dpitch,
                 uint8_t* __restrict__ dstPacked3, double scaleX, double scaleY) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  // source coordinate and 11-bit taps depend on the column (row) only: evaluated once per block (32 x 8 threads)
+  __shared__ int sSx[32], sSy[8], sAx[32][4], sBy[8][4];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
+  if (ty == 0) cubicTaps11(min(x, dw - 1), scaleX, sSx[tx], sAx[tx]);
+  else if (ty == 1 && tx < 8) cubicTaps11(min((int)blockIdx.y * 8 + tx, dh - 1), scaleY, sSy[tx], sBy[tx]);
+  __syncthreads();
   if (x >= dw || y >= dh) return;
-  int sx, sy, ax[4], by[4];
-  cubicTaps11(x, scaleX, sx, ax);
-  cubicTaps11(y, scaleY, sy, by);
+  const int sx = sSx[tx], sy = sSy[ty];
+  int ax[4], by[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { ax[j] = sAx[tx][j]; by[j] = sBy[ty][j]; }
   int rows[4][4];  // [tap row][channel]
 #pragma unroll
   for (int r = 0; r < 4; ++r) {

@@ -12,7 +12,7 @@ samples each (window of output j: rows j..j+4):
 The merge networks are Batcher odd-even merges, padded with +inf, pruned by liveness, dead halves of
 compare-exchanges dropped and chains min(min(a,b),c) fused into the 3-input FMNMX3 (PTX min.f32 a,b,c).
 Every piece is verified here: merges on all sorted 0/1 inputs (0/1 principle) and the whole run against
-sorted()[12] on random and tie-heavy inputs.  Usage: python tools/gen_median_run.py > csrc/median_run.inc
+sorted()[12] on random and tie-heavy inputs.  Usage: python tools/gen_median_run.py [R] > csrc/median_run.inc   (R medians per thread, default 4; 8 -> median_run8.inc)
 """
 import itertools, random, sys
 
@@ -84,14 +84,18 @@ def sel6(bd, A6, B5):
     t5 = bd.new(); bd.ops.append((t5, 'min', t4, terms[5]))
     return t5
 
-def build():
+def build(R=4):
+    """R (even) vertically adjacent medians from R + 4 rows."""
     bd = Builder()
-    rows = [[f'v{r}{c}' for c in range(5)] for r in range(8)]
-    S = [sort5(bd, rows[r]) for r in range(8)]
-    P = {r: merge_sorted(bd, S[r], S[r + 1]) for r in (1, 3, 5)}
-    Q = {r: merge_sorted(bd, P[r], P[r + 2])[7:13] for r in (1, 3)}
-    outs = [sel6(bd, Q[1], S[0]), sel6(bd, Q[1], S[5]), sel6(bd, Q[3], S[2]), sel6(bd, Q[3], S[7])]
+    rows = [[f'v{r}_{c}' for c in range(5)] for r in range(R + 4)]
+    S = [sort5(bd, rows[r]) for r in range(R + 4)]
+    P = {r: merge_sorted(bd, S[r], S[r + 1]) for r in range(1, R + 2, 2)}
+    Q = {r: merge_sorted(bd, P[r], P[r + 2])[7:13] for r in range(1, R, 2)}
+    outs = []
+    for j in range(R):   # window of output j: rows j .. j+4
+        outs.append(sel6(bd, Q[j + 1], S[j]) if j % 2 == 0 else sel6(bd, Q[j], S[j + 4]))
     return bd.ops, outs
+
 
 def dce(ops, outs):
     live = set(outs)
@@ -134,8 +138,9 @@ def evaluate(ops, outs, env):
     return [env[o] for o in outs]
 
 def verify(ops, outs):
+    R = len(outs)
     rng = random.Random(7)
-    names = [f'v{r}{c}' for r in range(8) for c in range(5)]
+    names = [f'v{r}_{c}' for r in range(R + 4) for c in range(5)]
     for trial in range(20000):
         mode = trial % 4
         if mode == 0: vals = [rng.random() for _ in names]
@@ -144,8 +149,8 @@ def verify(ops, outs):
         else: vals = [rng.randint(-50, 50) for _ in names]
         env = dict(zip(names, vals))
         got = evaluate(ops, outs, env)
-        for j in range(4):
-            win = sorted(env[f'v{r}{c}'] for r in range(j, j + 5) for c in range(5))
+        for j in range(R):
+            win = sorted(env[f'v{r}_{c}'] for r in range(j, j + 5) for c in range(5))
             assert got[j] == win[12], (trial, j, got[j], win[12])
     # merges: all sorted 0/1 inputs (0/1 principle for merging networks)
     for na, nb in ((5, 5), (10, 10)):
@@ -161,19 +166,20 @@ def verify(ops, outs):
 def emit(ops, outs):
     print('// generated by tools/gen_median_run.py -- do not edit')
     n2 = sum(1 for op in ops if len(op) == 4); n3 = len(ops) - n2
-    print(f'// {len(ops)} min/max instructions for four medians ({n2} two-input, {n3} three-input)')
-    for r in range(8):
-        print(' '.join(f'const float v{r}{c} = v[{r}][{c}];' for c in range(5)))
+    print(f'// {len(ops)} min/max instructions for {len(outs)} medians ({n2} two-input, {n3} three-input)')
+    for r in range(len(outs) + 4):
+        print(' '.join(f'const float v{r}_{c} = v[{r}][{c}];' for c in range(5)))
     for dst, kind, *args in ops:
         if len(args) == 2:
             print(f'const float {dst} = {"fminf" if kind == "min" else "fmaxf"}({args[0]}, {args[1]});')
         else:
             print(f'const float {dst} = {"min3f" if kind == "min3" else "max3f"}({args[0]}, {args[1]}, {args[2]});')
     for j, o in enumerate(outs):
-        print(f'out{j} = {o};')
+        print(f'out[{j}] = {o};')
 
 if __name__ == '__main__':
-    ops, outs = build()
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    ops, outs = build(R)
     raw = len(ops)
     ops = dce(ops, outs)
     live = len(ops)
