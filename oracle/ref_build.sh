@@ -1,0 +1,39 @@
+#!/bin/bash
+# ORACLE — TEST INFRASTRUCTURE ONLY. Builds oracle/_ref/ from the reference's OWN sources, compiled where they lie
+# under /root/reference (nothing is copied into the repo), against the third-party stand-ins in oracle/ref_shim/
+# (OpenCV, Eigen, gflags, glog, folly are absent from this image; the OpenCV image primitives forward to the
+# cv2-pinned oracle/ocv.h). Outputs (git-ignored, shipped to the GPU box with the snapshot):
+#   oracle/_ref/TestRenderStereoPanorama   the reference's frame renderer (its own main(), flags, threading, file I/O)
+#   oracle/_ref/libref.so                  the reference's operators behind a small C API (oracle/ref_capi.cpp)
+# Flags follow the reference's build (surround360_render/CMakeLists.txt: -O3 -std=c++11 -mavx, no -mfma, threads).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF=${S360_REFERENCE_ROOT:-/root/reference}/surround360_render/source
+if [ ! -d "$REF" ]; then echo "ref_build: $REF not found (prebuilt oracle/_ref is used as is)"; exit 0; fi
+OUT="$HERE/_ref"
+mkdir -p "$OUT/obj"
+CXX=${REF_CXX:-/usr/bin/g++}   # not $CXX: the image presets it to a toolchain that links libstdc++ statically (two C++ runtimes in one python process)
+CXXFLAGS="-m64 -O3 -mmmx -mavx -msse -msse3 -funroll-loops -pipe -std=c++14 -pthread -fPIC -w -g"
+INC="-I$HERE/ref_shim -I$REF/util -I$REF/render -I$REF/optical_flow -I$REF/calibration -I$REF"
+SRCS="util/CvUtil.cpp util/SystemUtil.cpp util/StringUtil.cpp render/Camera.cpp render/ImageWarper.cpp render/PoleRemoval.cpp render/RigDescription.cpp optical_flow/NovelView.cpp"
+OBJS=""
+pids=""
+for s in $SRCS; do
+  o="$OUT/obj/$(echo $s | tr '/' '_' | sed 's/\.cpp$/.o/')"
+  OBJS="$OBJS $o"
+  if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ] || [ -n "$(find "$HERE/ref_shim" "$HERE/ocv.h" -newer "$o" -print -quit)" ]; then
+    $CXX $CXXFLAGS $INC -c "$REF/$s" -o "$o" &
+    pids="$pids $!"
+  fi
+done
+o="$OUT/obj/ref_shim.o"; OBJS="$OBJS $o"
+$CXX $CXXFLAGS $INC -c "$HERE/ref_shim/ref_shim.cpp" -o "$o" &
+pids="$pids $!"
+$CXX $CXXFLAGS $INC -c "$REF/test/TestRenderStereoPanorama.cpp" -o "$OUT/obj/trsp_main.o" &
+pids="$pids $!"
+$CXX $CXXFLAGS $INC -c "$HERE/ref_capi.cpp" -o "$OUT/obj/ref_capi.o" &
+pids="$pids $!"
+for p in $pids; do wait $p; done
+$CXX -pthread -o "$OUT/TestRenderStereoPanorama" "$OUT/obj/trsp_main.o" $OBJS -lz
+$CXX -pthread -shared -o "$OUT/libref.so" "$OUT/obj/ref_capi.o" $OBJS -lz
+echo "ref_build: built $OUT/TestRenderStereoPanorama and $OUT/libref.so"
