@@ -72,6 +72,27 @@ def test_stage_eyes_and_outputs(ctx, rendered):
     close(cube, ref.get("cubemap"), "cubemap")
 
 
+def test_outputs_match_the_reference_build(ctx, rendered, frames17):
+    """The CUDA frame against the REFERENCE'S OWN CODE (oracle/_ref: TestRenderStereoPanorama.cpp & co. compiled unchanged,
+    oracle/ref_build.sh), not only against the restatement: equirect, cubemap and flows, 0 LSB."""
+    import ref_bind as rb
+    from conftest import RIG17
+    if not rb.available():
+        pytest.skip("oracle/_ref not built")
+    eq, cube, _ = rendered
+    r = rb.Frame(RIG17, frames17, rb.make_params(**SMALL))
+    try:
+        close(eq, r.equirect, "equirect vs reference build")
+        close(cube, r.cubemap, "cubemap vs reference build")
+        for i in (0, 7, 13):
+            close(ctx.intermediate("flowLtoR", i), r.flow(f"flowLtoR_{i}"), f"flowLtoR {i} vs reference build")
+            close(ctx.intermediate("flowRtoL", i), r.flow(f"flowRtoL_{i}"), f"flowRtoL {i} vs reference build")
+        for k, n in enumerate(("top_left", "top_right", "bottom_left", "bottom_right")):
+            close(ctx.intermediate("poleFlow", k), r.flow("flow_" + n), f"pole flow {n} vs reference build")
+    finally:
+        r.close()
+
+
 def test_side_only_no_sharpen_no_resize(ctx, orig, frames17):
     kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1400, final_eqr_height=1400)   # resize guard of TRSP:938-941 -> skipped
     eq = ctx.renderStereoPanorama(api.default_params(**kw), frames17)

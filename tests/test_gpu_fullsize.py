@@ -70,6 +70,17 @@ def test_config2_6k_matches_oracle(orig, frames17):
         eq = _check_all(c, out, ref, cubemap=False)
         assert eq.shape == (6144, 6144, 3)
         assert np.array_equal(eq[:3072], ref.get("equirect")[:3072])       # the left-eye ("mono") half on its own
+        # and against the reference's own code at this size (oracle/_ref, built from /root/reference by oracle/ref_build.sh)
+        import ref_bind as rb
+        from conftest import RIG17
+        if rb.available():
+            kw = dict(sharpening=0.25, enable_top=1, enable_bottom=1, **api.PRESETS["6k"])
+            r = rb.Frame(RIG17, frames17, rb.make_params(**kw))
+            try:
+                _diff(eq, r.equirect, "equirect vs the reference build (6K)")
+                _diff(c.intermediate("poleFlow", 2), r.flow("flow_bottom_left"), "pole flow vs the reference build (6K)")
+            finally:
+                r.close()
     finally:
         c.close()
 
