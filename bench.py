@@ -9,7 +9,7 @@ free HBM); `value` is frames/s. With N GPUs each rank renders its own batches (w
 only collective is one NCCL broadcast of the serialised rig at start-up.
 
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-  python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port) on host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref) on the host cores, same config
 """
 import argparse
 import json
@@ -103,48 +103,145 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The CPU arm: the reference's own implementation of the path on the host cores.
+#   kind "reference": oracle/_ref/libref.so = TestRenderStereoPanorama.cpp, PixFlow.h, NovelView.cpp, CvUtil.cpp, Filter.h,
+#                     ImageWarper.cpp, PoleRemoval.cpp, Camera.cpp ... compiled UNCHANGED from /root/reference (oracle/ref_build.sh;
+#                     the absent OpenCV primitives come from the cv2-pinned oracle/ocv.h);
+#   kind "port":      the oracle restatement (oracle/liboracle.so), used only when oracle/_ref was not built.
+# Same preset and flags as the CUDA arm (never a smaller preset). A step = one frame; the reference threads a frame the way
+# TestRenderStereoPanorama does (one thread per camera pair, 4 pole threads, 2 sharpen threads), which leaves most of a big
+# host idle, so P frames are rendered concurrently (one process each) to use all the host threads it can.
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_arm_kind():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_bind
+    return "reference" if ref_bind.available() else "port"
+
+
+def cpu_arm_worker(args):
+    """One worker process: renders frames on request. Protocol on stdin/stdout: 'READY' -> ('GO n' -> 'DONE seconds maxrss_kb')*."""
+    import resource
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    kw = preset_kwargs(args.preset, args.cubemap)
+    frames = list(np.load(args.frames_npy, mmap_mode="r"))
+    if args.worker_kind == "reference":
+        import ref_bind as rb
+        p = rb.make_params(**kw)
+        render = lambda: rb.Frame(args.rig, frames, p).close()
+    else:
+        import oracle_bind as ob
+        rig = ob.Rig.load(args.rig)
+        p = ob.make_params(threads=1, **kw)
+        render = lambda: rig.render_frame(frames, p)
+    print("READY", flush=True)
+    for line in sys.stdin:
+        f = line.split()
+        if not f or f[0] != "GO":
+            break
+        t0 = time.perf_counter()
+        for _ in range(int(f[1])):
+            render()
+        print("DONE", time.perf_counter() - t0, resource.getrusage(resource.RUSAGE_SELF).ru_maxrss, flush=True)
+
+
+def run_cpu_arm(preset, cubemap, steps, warmup, rig_path, frames, max_procs=None):
+    """-> dict(frames_per_s, seconds, procs, kind, maxrss_gb). `steps` timed frames after `warmup` untimed ones."""
+    kind = cpu_arm_kind()
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        mem_gb = psutil.virtual_memory().available / 2**30
+    except Exception:
+        mem_gb = 64.0
+    per_frame_gb = {"8k": 24.0, "6k": 14.0, "4k": 5.0, "3k": 5.0}[preset]      # resident set of one reference frame, with margin (8k measured: see DESIGN.md)
+    procs = max(1, min(steps, cores // 10, int(mem_gb * 0.6 // per_frame_gb), max_procs or 10**6))
+    npy = f"/dev/shm/s360_cpu_arm_frames_{os.getpid()}.npy" if os.path.isdir("/dev/shm") else f"/tmp/s360_cpu_arm_frames_{os.getpid()}.npy"
+    np.save(npy, np.stack(frames))
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-arm-worker", "--preset", preset, "--worker-kind", kind, "--rig", rig_path,
+           "--frames-npy", npy] + (["--cubemap"] if cubemap else [])
+    workers = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1) for _ in range(procs)]
+    try:
+        for w in workers:
+            if w.stdout.readline().strip() != "READY":
+                raise RuntimeError("cpu arm worker failed to start")
+
+        def round_(total):
+            per = [total // procs + (1 if i < total % procs else 0) for i in range(procs)]
+            t0 = time.perf_counter()
+            for w, n in zip(workers, per):
+                if n:
+                    w.stdin.write(f"GO {n}\n"); w.stdin.flush()
+            rss = 0
+            for w, n in zip(workers, per):
+                if n:
+                    f = w.stdout.readline().split()
+                    if not f or f[0] != "DONE":
+                        raise RuntimeError("cpu arm worker died")
+                    rss = max(rss, int(f[2]))
+            return time.perf_counter() - t0, rss
+
+        if warmup:
+            round_(warmup)
+        dt, rss = round_(steps)
+    finally:
+        for w in workers:
+            try:
+                w.stdin.close()
+            except Exception:
+                pass
+        for w in workers:
+            try:
+                w.wait(timeout=30)
+            except Exception:
+                w.kill()
+        try:
+            os.remove(npy)
+        except OSError:
+            pass
+    return dict(frames_per_s=steps / dt, seconds=dt, procs=procs, kind=kind, cores=cores, maxrss_gb=rss / 2**20)
+
+
+def cpu_arm_sample_text(r, preset, steps):
+    src = ("the reference's own sources compiled unchanged (oracle/_ref, OpenCV primitives from the cv2-pinned oracle/ocv.h)" if r["kind"] == "reference"
+           else "oracle port of the reference (oracle/_ref not built)")
+    return (f"{steps} frame(s) of the '{preset}' preset in {r['seconds']:.1f} s wall: {r['procs']} frame(s) at a time, each threaded like "
+            f"TestRenderStereoPanorama (one thread per camera pair, 4 pole threads, 2 sharpen threads); {src}")
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path (oracle port, reference threading shape)
-    on the host cores. Rank 0 only."""
+    """`--impl reference`: the CPU arm on the same config, metric and unit as the CUDA arm. Rank 0 only."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_bind as ob
     from surround360_b200 import rig_gen
     rig_path = "/tmp/s360_bench_rig.json"
     rig_gen.write_rig(rig_path)
-    total_steps = args.steps + args.warmup
-    # bounded sample: a full 8K frame costs ~1 minute of CPU; if more than 3 frames would be
-    # needed, each step renders the "4k" preset frame instead and the value is converted through
-    # output megapixels (the metric's other unit) to 8K frames/s.
-    sample = "8k" if total_steps <= 3 else "4k"
-    kw = preset_kwargs(sample)
-    p = ob.make_params(threads=1, **kw)
-    rig = ob.Rig.load(rig_path)
     frames = make_frames(rig_path, 1)[0]
+    kw = preset_kwargs(args.preset, args.cubemap)
+    r = run_cpu_arm(args.preset, args.cubemap, args.steps, args.warmup, rig_path, frames)
+    value = r["frames_per_s"]
     out_mp = kw["final_eqr_width"] * kw["final_eqr_height"] / 1e6
-    for _ in range(args.warmup):
-        rig.render_frame(frames, p)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rig.render_frame(frames, p)
-    dt = time.perf_counter() - t0
-    mp_s = out_mp * args.steps / dt
-    value = mp_s / OUT_MP_PER_FRAME
-    cores = os.cpu_count()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
-        "config": {"workload": "17-cam rig, 2048x2048 synthetic RGBA frames -> 8K stereo equirect (8k preset, top+bottom, pixflow_low)",
-                   "sample": sample},
-        "mp_per_s": mp_s,
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} frame(s) of the '{sample}' preset, reference threading (14 pair / 4 pole / 2 sharpen threads)"
-                                   + ("" if sample == "8k" else ", converted to 8K frames/s by output megapixels")},
+        "config": workload_config(args.preset, args.cubemap, args.inflight, max(world, 1)),
+        "mp_per_s": value * out_mp,
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": "each step = 1 frame of the step's batch; " + cpu_arm_sample_text(r, args.preset, args.steps),
+                         "concurrent_frames": r["procs"], "max_rss_gb_per_frame": r["maxrss_gb"]},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(preset, cubemap, frames_per_step, world):
+    """The `config` block: identical in both arms (the reference arm times a bounded sample of this workload)."""
+    return {"workload": f"17-cam rig, 2048x2048 synthetic frames -> 8K stereo equirect ({preset} preset, top+bottom, pixflow_low"
+                        + (", +cubemap 1536" if cubemap else "") + ")",
+            "frames_per_step": frames_per_step, "frames_in_flight_per_gpu": frames_per_step,
+            "l2": "inputs (214 MB/frame) exceed the 126 MB L2; two alternating input sets",
+            "parallelism": f"frames sharded one-per-GPU x{world}, single NCCL broadcast of the rig"}
 
 
 def main():
@@ -158,7 +255,15 @@ def main():
     ap.add_argument("--inflight", type=int, default=20, help="frames in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short 6k / cubemap passes appended to the headline line")
+    ap.add_argument("--cpu-arm-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--worker-kind", default="reference", help=argparse.SUPPRESS)
+    ap.add_argument("--rig", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--frames-npy", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_arm_worker:
+        cpu_arm_worker(args)
+        return
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
 
@@ -348,28 +453,19 @@ def main():
                 "note": "dependency-latency-bound recurrence: reported against the HBM roofline for completeness"}
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_bind as ob
-        orig = ob.Rig.load(rig_path)
-        # bounded sample: one frame of the '6k' preset (~25 s of CPU on 8 cores), converted by output megapixels
-        skw = preset_kwargs("6k")
-        op = ob.make_params(threads=1, **skw)
-        t0 = time.perf_counter()
-        orig.render_frame(frame_sets[0], op)
-        dt = time.perf_counter() - t0
-        mp_s = skw["final_eqr_width"] * skw["final_eqr_height"] / 1e6 / dt
-        cpu_baseline = {"value": mp_s / OUT_MP_PER_FRAME, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"1 frame of the '6k' preset ({dt:.1f} s wall, reference threading shape), converted to 8K frames/s by output megapixels"}
+    if not args.no_cpu_baseline and world == 1:
+        # bounded sample on the host cores, in worker processes of their own (the GPU arm's process never loads the CPU code):
+        # one round of concurrent frames of the same preset
+        P = max(1, min((os.cpu_count() or 1) // 10, 12))
+        r = run_cpu_arm(args.preset, args.cubemap, P, 0, rig_path, frame_sets[0], max_procs=P)
+        cpu_baseline = {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"],
+                        "sample": cpu_arm_sample_text(r, args.preset, P), "concurrent_frames": r["procs"], "max_rss_gb_per_frame": r["maxrss_gb"]}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32", "data": "synthetic",
-        "config": {"workload": f"17-cam rig, 2048x2048 synthetic frames -> 8K stereo equirect ({args.preset} preset, top+bottom, pixflow_low"
-                               + (", +cubemap 1536" if args.cubemap else "") + ")",
-                   "frames_per_step": F, "frames_in_flight_per_gpu": F, "l2": "inputs (214 MB/frame) exceed the 126 MB L2; two alternating input sets",
-                   "parallelism": f"frames sharded one-per-GPU x{world}, single NCCL broadcast of the rig"},
+        "config": workload_config(args.preset, args.cubemap, F, world),
         "mp_per_s": value * eq_w * eq_h / 1e6,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline,
         "stage_ms_single_frame": stage_ms, "host_enqueue_ms_per_frame": 1000.0 * t_enq / (args.steps * F),

@@ -202,6 +202,16 @@ struct Camera {
     r.m[2][0] = b.x; r.m[2][1] = b.y; r.m[2][2] = b.z;
     r.m[1][0] = upv.x; r.m[1][1] = upv.y; r.m[1][2] = upv.z;
     r.m[0][0] = rightv.x; r.m[0][1] = rightv.y; r.m[0][2] = rightv.z;
+    // CHECK(rotation.isUnitary(0.001)), Camera.cpp:24-26 (Eigen: unit columns, |n - 1| <= min(n, 1) tol; orthogonal columns, |dot| <= tol)
+    const double tol = 0.001;
+    for (int i = 0; i < 3; ++i) {
+      const double n = r.m[0][i] * r.m[0][i] + r.m[1][i] * r.m[1][i] + r.m[2][i] * r.m[2][i];
+      if (!(std::fabs(n - 1.0) <= (std::fabs(n) < 1.0 ? std::fabs(n) : 1.0) * tol)) throw std::runtime_error("camera rotation is not close to unitary");
+      for (int j = 0; j < i; ++j) {
+        const double d = r.m[0][i] * r.m[0][j] + r.m[1][i] * r.m[1][j] + r.m[2][i] * r.m[2][j];
+        if (!(std::fabs(d) <= tol)) throw std::runtime_error("camera rotation is not close to unitary");
+      }
+    }
     rotation = reunitarize(r);
   }
   void setFov(double fov) {

@@ -229,6 +229,7 @@ int s360_set_pole_masks(s360_ctx* c, const uint8_t* m1, const uint8_t* m2, int w
   S360_CUDA_CHECK(cudaMemcpy(c->poleMasks.p, m1, bytes, cudaMemcpyHostToDevice));
   S360_CUDA_CHECK(cudaMemcpy(c->poleMasks.as<uint8_t>() + bytes, m2, bytes, cudaMemcpyHostToDevice));
   c->poleMaskW = w; c->poleMaskH = h;
+  resetPlan(c);   // the plan (and its captured graph) holds the mask pointers and sizes
   S360_API_END
 }
 int s360_geometry_query(s360_ctx* c, const s360_params* p, s360_geometry* out) {
@@ -494,10 +495,8 @@ int s360_flow_save(const char* path, const float* flow, int w, int h) {
   FILE* f = std::fopen(path, "wb");
   if (!f) throw std::runtime_error(std::string("file not found: ") + path);
   const int32_t rows = h, cols = w;
-  std::fwrite(&rows, 4, 1, f);
-  std::fwrite(&cols, 4, 1, f);
-  std::fwrite(flow, 8, (size_t)w * h, f);
-  std::fclose(f);
+  const bool ok = std::fwrite(&rows, 4, 1, f) == 1 && std::fwrite(&cols, 4, 1, f) == 1 && std::fwrite(flow, 8, (size_t)w * h, f) == (size_t)w * h;
+  if (std::fclose(f) != 0 || !ok) throw std::runtime_error(std::string("failed to write flow file: ") + path);
   S360_API_END
 }
 int s360_flow_load(const char* path, float** out, int* w, int* h) {

@@ -230,8 +230,9 @@ int run(int argc, char** argv) {
           saveIntermediateImage(ctx, "extSide", k, flowImagesDir + "/extendedSideSpherical_" + kPoleSlotNames[k] + ".png");
           saveIntermediateImage(ctx, "extFish", k, flowImagesDir + "/extendedFisheyeSpherical_" + kPoleSlotNames[k] + ".png");
         }
-    } else if (verbose) {
-      std::cerr << "flow image directory " << flowImagesDir << " does not exist; flow input images not saved\n";
+    } else {   // the reference fails here: imwriteExceptionOnFail (TRSP:203-208, util/CvUtil.cpp:44-52)
+      throw VrCamException("failed to write image: " + flowImagesDir + "/overlap_0_L.png (the directory does not exist; the driver script creates it, "
+                           "scripts/batch_process_video.py:116-118, or pass --save_flow_data=false)");
     }
     if (stat(flowDir.c_str(), &st) == 0) {  // directories are created by the driver script (batch_process_video.py:116-118)
       for (int i = 0; i < nSide; ++i) {
@@ -241,9 +242,35 @@ int run(int argc, char** argv) {
       for (int k = 0; k < 4; ++k)
         if ((k < 2 && P.enable_top) || (k >= 2 && P.enable_bottom))
           saveIntermediateFlow(ctx, "poleFlow", k, flowDir + "/flow_" + kPoleSlotNames[k] + ".bin");
-    } else if (verbose) {
-      std::cerr << "flow directory " << flowDir << " does not exist; flow data not saved\n";
+    } else {   // the reference fails here: saveFlowToFile (util/CvUtil.cpp:159-166)
+      throw VrCamException("file not found: " + flowDir + "/flowLtoR_0.bin (the directory does not exist; pass --save_flow_data=false to skip the flow files)");
     }
+  }
+  if (F.b("save_debug_images")) {
+    // The debug images the frame's kept intermediates provide (names as the reference writes them); the rest of the reference's
+    // debug dumps (croppedSideSpherical_*, eqr_side*.png before sharpening, bottomImage*.png of the pole removal) are not produced.
+    const std::string debugDir = outDir + "/debug/" + frame, projDir = debugDir + "/projections";
+    struct stat st;
+    if (stat(debugDir.c_str(), &st) != 0) throw VrCamException("failed to write image: " + debugDir + "/sphericalImgL.png");
+    if (stat(projDir.c_str(), &st) == 0) {   // TRSP:177-184
+      for (int i = 0; i < nSide; ++i) {
+        const char* id = s360_rig_camera_id(ctx, s360_rig_side_index(ctx, i));
+        saveIntermediateImage(ctx, "projection", i, projDir + "/crop_" + std::string(id ? id : "") + ".png");
+      }
+    } else {
+      throw VrCamException("failed to write image: " + projDir + "/crop_*.png");
+    }
+    saveIntermediateImage(ctx, "panoL", 0, debugDir + "/sphericalImgL.png");   // TRSP:792-793
+    saveIntermediateImage(ctx, "panoR", 0, debugDir + "/sphericalImgR.png");
+    if (P.enable_top) saveIntermediateImage(ctx, "topSpherical", 0, debugDir + "/_topSpherical.png");          // TRSP:680
+    if (P.enable_bottom) saveIntermediateImage(ctx, "bottomSpherical", 0, debugDir + "/_bottomSpherical.png");  // TRSP:639
+    for (int k = 0; k < 4; ++k)
+      if ((k < 2 && P.enable_top) || (k >= 2 && P.enable_bottom)) {
+        saveIntermediateImage(ctx, "poleWarped", k, debugDir + "/warpedSpherical_" + kPoleSlotNames[k] + ".png");        // TRSP:551-553
+        saveIntermediateImage(ctx, "extSide", k, debugDir + "/extendedSideSpherical_" + kPoleSlotNames[k] + ".png");     // TRSP:554-556
+      }
+    std::cerr << "note: --save_debug_images wrote projections/crop_*, sphericalImg{L,R}, _{top,bottom}Spherical, warpedSpherical_*, "
+                 "extendedSideSpherical_*; the reference's other debug dumps are not produced by this build\n";
   }
   if (verbose) {  // TRSP:964-971
     std::cerr << "--- Runtime breakdown (sec) ---\n";

@@ -216,7 +216,11 @@ struct FramePlan {
   bool graphHasCube = false, graphUsesPrev = false, lastWasTimed = false;
   unsigned long long graphLaunches = 0;
   bool valid = false;
-  ~FramePlan() { if (graphExec) cudaGraphExecDestroy(graphExec); }
+  bool evCreated = false;
+  ~FramePlan() {
+    if (graphExec) cudaGraphExecDestroy(graphExec);
+    if (evCreated) for (auto& e : ev) cudaEventDestroy(e);
+  }
 };
 
 static bool sameParams(const s360_params& a, const s360_params& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
@@ -304,6 +308,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
   F.sharpF = F.workspace.as<float>();
   F.sharpLp = reinterpret_cast<uchar4*>(F.workspace.as<uint8_t>() + eqPx * 3 * 4 * 2);
   for (auto& e : F.ev) S360_CUDA_CHECK(cudaEventCreate(&e));
+  F.evCreated = true;
   F.valid = true;
   c->plan = std::move(plan);
 }

@@ -1,5 +1,6 @@
 // Rig JSON parsing and the host camera model. See rig.h for the reference citations.
 #include "rig.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -124,12 +125,17 @@ Vec3 readVec3(const Json& j) { double v[3]; readVec(j, v, 3); return {v[0], v[1]
 void Camera::setRotation(Vec3 fwd, Vec3 upv, Vec3 rightv) {
   if (!(dot(cross(rightv, upv), fwd) < 0)) throw std::runtime_error("rotation must be right-handed");
   double m[3][3] = {{rightv.x, rightv.y, rightv.z}, {upv.x, upv.y, upv.z}, {-fwd.x, -fwd.y, -fwd.z}};
-  // unitary check with tolerance 0.001 like CHECK(rotation.isUnitary(tol))
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      double d = m[i][0] * m[j][0] + m[i][1] * m[j][1] + m[i][2] * m[j][2];
-      if (std::fabs(d - (i == j ? 1.0 : 0.0)) > 0.01) throw std::runtime_error("camera rotation is not close to unitary");
+  // CHECK(rotation.isUnitary(0.001)) (Camera.cpp:24-26), with Eigen's definition: every COLUMN has unit squared norm within
+  // |n - 1| <= min(n, 1) * tol, and distinct columns have |dot| <= tol
+  const double tol = 0.001;
+  for (int i = 0; i < 3; ++i) {
+    const double n = m[0][i] * m[0][i] + m[1][i] * m[1][i] + m[2][i] * m[2][i];
+    if (!(std::fabs(n - 1.0) <= std::min(std::fabs(n), 1.0) * tol)) throw std::runtime_error("camera rotation is not close to unitary");
+    for (int j = 0; j < i; ++j) {
+      const double d = m[0][i] * m[0][j] + m[1][i] * m[1][j] + m[2][i] * m[2][j];
+      if (!(std::fabs(d) <= tol)) throw std::runtime_error("camera rotation is not close to unitary");
     }
+  }
   double q[4];  // x y z w
   double tr = m[0][0] + m[1][1] + m[2][2];
   if (tr > 0) {

@@ -156,15 +156,19 @@ def test_cli_is_a_drop_in(ctx, frames17, tmp_path, rig_path):
         assert cv2.imwrite(str(imgs / cam["id"] / "000000.png"), im)
     out = tmp_path / "out"
     (out / "flow" / "000000").mkdir(parents=True)
+    (out / "debug" / "000000" / "flow_images").mkdir(parents=True)      # both created by the driver script (batch_process_video.py:116-118)
+    (out / "debug" / "000000" / "projections").mkdir(parents=True)
     kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1024, final_eqr_height=1024, sharpening=0.25, enable_top=1, enable_bottom=1)
     cmd = [exe, "--rig_json_file", rig_path, "--imgs_dir", str(imgs), "--frame_number", "000000", "--output_data_dir", str(out),
            "--prev_frame_data_dir", "NONE", "--output_equirect_path", str(out / "eqr.png"), "--output_cubemap_path", str(out / "cube.png"),
            "--cubemap_width=128", "--cubemap_height", "128", "--cubemap_format", "photo", "--enable_top", "--enable_bottom=true",
            "--sharpening", "0.25", "--eqr_width", "1400", "--eqr_height", "700", "--final_eqr_width", "1024", "--final_eqr_height", "1024",
-           "--v", "1", "--logbuflevel", "-1", "--stderrthreshold", "0"]
+           "--v", "1", "--logbuflevel", "-1", "--stderrthreshold", "0", "--save_debug_images"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "--- Runtime breakdown (sec) ---" in r.stderr and "Side optical flow:" in r.stderr
+    crop = cv2.imread(str(out / "debug" / "000000" / "projections" / f"crop_{[c for c in rig['cameras'] if 'side' in c.get('group', '')][0]['id']}.png"), cv2.IMREAD_UNCHANGED)
+    assert crop is not None and crop.shape[2] == 4 and os.path.exists(out / "debug" / "000000" / "sphericalImgL.png")
     eq_cli = cv2.imread(str(out / "eqr.png"), cv2.IMREAD_COLOR)
     cube_cli = cv2.imread(str(out / "cube.png"), cv2.IMREAD_COLOR)
     eq, cube = ctx.renderStereoPanorama(api.default_params(want_cubemap=1, cubemap_photo=1, cubemap_width=128, cubemap_height=128, **kw), frames17)
@@ -175,6 +179,13 @@ def test_cli_is_a_drop_in(ctx, frames17, tmp_path, rig_path):
     # error behaviour: unknown flow algorithm -> VrCamException text, non-zero exit
     r = subprocess.run(cmd + ["--side_flow_alg", "nope"], capture_output=True, text=True)
     assert r.returncode != 0 and "unrecognized flow algorithm name: nope" in r.stderr
+    # missing output directories fail like imwriteExceptionOnFail / saveFlowToFile do in the reference
+    import shutil
+    shutil.rmtree(out / "flow")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode != 0 and "file not found" in r.stderr
+    r = subprocess.run(cmd + ["--save_flow_data=false", "--nosave_debug_images"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
 
 
 def test_pole_removal(ctx, orig, frames17):
