@@ -66,6 +66,7 @@ int s360_ctx_synchronize(s360_ctx* c) {
   S360_API_BEGIN
   useDevice(c);
   S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  checkFlowErrors(c);
   S360_API_END
 }
 void* s360_ctx_stream(s360_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -150,7 +151,7 @@ int s360_profile_sweep(s360_ctx* c, double* ms, unsigned long long* launches, do
 int s360_profile_sweep_fallbacks(s360_ctx* c, unsigned long long* fallbacks) {
   S360_API_BEGIN
   require(c != nullptr && fallbacks != nullptr, "null argument");
-  *fallbacks = c->sweepProfile.fallbacks;   // filled by the last s360_profile_sweep
+  *fallbacks = c->sweepProfile.fallbacks;   // kept for ABI stability: always 0 since the fast/generic sweep pair was removed
   S360_API_END
 }
 
@@ -295,6 +296,7 @@ int s360_flow_compute_batch(s360_ctx* c, const char* alg, int n, const uint8_t* 
   fb.run(st, ip, pv, dF.as<float2>());
   for (int k = 0; k < n; ++k) S360_CUDA_CHECK(cudaMemcpyAsync(flowOut[k], dF.as<float2>() + k * px, px * 8, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  fb.checkSweepError();
   S360_API_END
 }
 
@@ -325,6 +327,7 @@ int s360_flow_compute(s360_ctx* c, const char* alg, const uint8_t* i0, const uin
   fb.run(st, ip, pv, dF.as<float2>());
   S360_CUDA_CHECK(cudaMemcpyAsync(flowOut, dF.p, px * 8, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  fb.checkSweepError();
   S360_API_END
 }
 

@@ -153,6 +153,8 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   void enableProfile(bool on) { profile_ = on; }
   // call after the stream has been synchronised; accumulates and clears pending events
   void collectProfile(SweepProfile* acc);
+  // after the stream has been synchronised: throws if a sweep band gave up waiting for its producer (see k_sweep's bounded spin)
+  void checkSweepError();
 
  private:
   int n_, w_, h_, dw_, dh_;
@@ -166,6 +168,7 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   std::vector<ProfRec> pending_;
   std::vector<cudaEvent_t> evPool_;
   cudaEvent_t getEvent();
+  void buildResizeTabs();
   std::vector<float2*> dumpBuf_;
   // device buffers (per level, batched over n)
   std::vector<float*> I0_, I1_, A0_, A1_;
@@ -176,7 +179,17 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   uchar4* small1_ = nullptr;
   float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
-  int* sweepBad_ = nullptr;
+  int* sweepErr_ = nullptr;
+  // frame-invariant resize coordinates / weights per pyramid level, tabulated on the host once (flow_kernels.cu: ResizeTabs)
+  void* tabAlloc_ = nullptr;
+  std::vector<const int*> cubSx_, cubSy_;      // [l]: cubic upsample level l+1 -> l
+  std::vector<const float4*> cubAx_, cubBy_;
+  const int *downSx_ = nullptr, *downSy_ = nullptr;   // 8-bit cubic downscale full size -> working size
+  const int4 *downAx_ = nullptr, *downBy_ = nullptr;
+  const float4* downFby_ = nullptr;
+  std::vector<const int*> linSx_, linSy_;      // [l]: linear pyramid level l-1 -> l; [0]: the final upscale to the full size
+  std::vector<const float*> linFx_, linFy_;
+  size_t boundaryElems_ = 0;
   void* arena_ = nullptr;
   void* boundaryAlloc_ = nullptr;
   bool bound_ = false;

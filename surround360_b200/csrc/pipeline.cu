@@ -591,6 +591,7 @@ void renderFrameHost(s360_ctx* c, const s360_params& P, const uint8_t* const* im
   S360_CUDA_CHECK(cudaMemcpyAsync(equirect, F.outEq.p, (size_t)oW * oH * 3, cudaMemcpyDeviceToHost, st));
   if (wantCube) S360_CUDA_CHECK(cudaMemcpyAsync(cubemap, F.outCube.p, (size_t)cW * cH * 3, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  checkFlowErrors(c);
   if (!F.lastWasTimed) return;   // graph replay: no per-stage events
   // stage times of this frame
   FramePlan& G = *c->plan;
@@ -764,6 +765,12 @@ void poleToSide(s360_ctx* c, const s360_params& P, const uint8_t* sideHost, int 
 namespace s360 {
 void resetPlan(s360_ctx* c) { c->plan.reset(); }
 void resetTemporal(s360_ctx* c) { if (c->plan) c->plan->prevValid = false; }
+void checkFlowErrors(s360_ctx* c) {   // call after the context's stream has been synchronised
+  if (!c->plan) return;
+  if (c->plan->sideFlow) c->plan->sideFlow->checkSweepError();
+  if (c->plan->poleFlowBatch) c->plan->poleFlowBatch->checkSweepError();
+  if (c->plan->prFlowBatch) c->plan->prFlowBatch->checkSweepError();
+}
 void collectProfile(s360_ctx* c) {
   if (!c->plan) return;
   S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -81,4 +81,5 @@ void poleToSide(s360_ctx* c, const s360_params& p, const uint8_t* sideHost, int 
                 uint8_t* warpedOut, float* flowOut);
 std::vector<int> gaussKernelFixed8(int n, double sigma);
 void collectProfile(s360_ctx* c);
+void checkFlowErrors(s360_ctx* c);
 }  // namespace s360

@@ -61,6 +61,7 @@ static inline unsigned __vminu2(unsigned a, unsigned b) {
   return std::min(a & 0xffffu, b & 0xffffu) | (std::min(a >> 16, b >> 16) << 16);
 }
 static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 using std::max;
 using std::min;
 static inline int min(int a, unsigned b) { return (int)std::min<long long>(a, b); }
@@ -69,6 +70,7 @@ static inline unsigned min(unsigned a, int b) { return (unsigned)std::min<long l
 namespace emu {
 void syncthreads();
 float shfl_up(float v, unsigned delta);
+float shfl_down(float v, unsigned delta);
 int shfl_idx(int v, int lane);
 float2 ld_volatile(const float2* p);
 void st_volatile(float2* p, float2 v);
@@ -77,6 +79,7 @@ void launch(const char* name, dim3 grid, dim3 block, Mode mode, const std::funct
 }  // namespace emu
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline float __shfl_up_sync(unsigned, float v, unsigned d) { return emu::shfl_up(v, d); }
+static inline float __shfl_down_sync(unsigned, float v, unsigned d) { return emu::shfl_down(v, d); }
 static inline int __shfl_sync(unsigned, int v, int lane) { return emu::shfl_idx(v, lane); }
 
 // ---- runtime API subset (device memory is host memory) ----
@@ -92,6 +95,7 @@ static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; 
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }

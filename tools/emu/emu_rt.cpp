@@ -25,6 +25,7 @@ struct Fiber {
   unsigned delta = 0;
   int srcLane = 0;
   bool isFloatShfl = true;
+  bool down = false;     // __shfl_down_sync
 };
 struct Group {           // fibers scheduled together on one OS thread: a block (BLOCK_BARRIER) or a warp (GRID_WARPS)
   std::vector<Fiber> fibers;
@@ -93,7 +94,7 @@ void runGroup(Group& g) {
           Fiber& f = g.fibers[i];
           if (f.state != AT_SHFL) continue;
           const int l = i - b;
-          if (f.isFloatShfl) f.fval = l >= (int)f.delta ? fv[l - f.delta] : fv[l];
+          if (f.isFloatShfl) f.fval = f.down ? (l + (int)f.delta < e - b ? fv[l + f.delta] : fv[l]) : (l >= (int)f.delta ? fv[l - f.delta] : fv[l]);
           else f.ival = iv[f.srcLane & 31];
           f.state = READY;
         }
@@ -120,9 +121,15 @@ Group makeGroup(dim3 grid, dim3 block, const std::function<void()>& body, unsign
 }  // namespace
 
 void syncthreads() { switchToScheduler(AT_BARRIER); }
+float shfl_down(float v, unsigned d) {
+  Fiber* f = tlFiber;
+  f->fval = v; f->delta = d; f->isFloatShfl = true; f->down = true;
+  switchToScheduler(AT_SHFL);
+  return f->fval;
+}
 float shfl_up(float v, unsigned d) {
   Fiber* f = tlFiber;
-  f->fval = v; f->delta = d; f->isFloatShfl = true;
+  f->fval = v; f->delta = d; f->isFloatShfl = true; f->down = false;
   switchToScheduler(AT_SHFL);
   return f->fval;
 }
