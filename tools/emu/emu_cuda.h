@@ -78,6 +78,7 @@ enum Mode { SEQUENTIAL, BLOCK_BARRIER, GRID_WARPS };
 void launch(const char* name, dim3 grid, dim3 block, Mode mode, const std::function<void()>& body);
 }  // namespace emu
 static inline void __syncthreads() { emu::syncthreads(); }
+static inline void __nanosleep(unsigned) {}
 static inline float __shfl_up_sync(unsigned, float v, unsigned d) { return emu::shfl_up(v, d); }
 static inline float __shfl_down_sync(unsigned, float v, unsigned d) { return emu::shfl_down(v, d); }
 static inline int __shfl_sync(unsigned, int v, int lane) { return emu::shfl_idx(v, lane); }
