@@ -28,11 +28,17 @@ import numpy as np
 METRIC = "8k_stereo_equirect_frames_per_sec"
 ALGO_BYTES_PER_LEVELPX_PER_SWEEP = 48.0  # "2 sweeps 96 B / level-px"
 OUT_MP_PER_FRAME = 8192 * 8192 / 1e6
-# dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch from the committed ncu --set full capture
-# (profiles/sweep_r1_final_raw.csv: finest side level, 28 flows x 607x884, algorithmic 48 B x 15.02 Mpx = 721 MB)
-NCU_SWEEP_TRAFFIC_BYTES = 871.9e6
-NCU_SWEEP_TRAFFIC_NOTE = "ncu capture of the finest side-level launch (3.12 ms; algorithmic bytes of that launch: 721 MB); " \
-                         "`achieved` averages over all 134 sweep launches of a frame"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/r2_dominant_kernel_traffic.json, written by tools/ncu_table.py --traffic from the raw CSV next to it); None without it."""
+    p = os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json")
+    try:
+        j = json.load(open(p))
+        return float(j["dram_bytes_per_launch"]), j.get("note", "")
+    except Exception:
+        return None, "no ncu capture committed for this tree"
 
 
 def preset_kwargs(name, cubemap=False):
@@ -244,6 +250,45 @@ def workload_config(preset, cubemap, frames_per_step, world):
             "parallelism": f"frames sharded one-per-GPU x{world}, single NCCL broadcast of the rig"}
 
 
+def side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cubemap, F, steps):
+    """A short device-resident throughput pass of another BASELINE config (frames in flight = F)."""
+    params = api.default_params(**preset_kwargs(preset, cubemap))
+    ctxs = []
+    for _ in range(F):
+        c = api.Context(local_rank)
+        c.load_rig_blob(blob_host)
+        ctxs.append(c)
+    eq_w, eq_h, cw, ch = ctxs[0].output_size(params)
+    img_h, img_w = frame_sets[0][0].shape[:2]
+    dev_in = [[torch.from_numpy(im).to(dev) for im in fs] for fs in frame_sets]
+    outs = [torch.empty((eq_h, eq_w, 3), dtype=torch.uint8, device=dev) for _ in range(F)]
+    cubes = [torch.empty((max(ch, 1), max(cw, 1), 3), dtype=torch.uint8, device=dev) for _ in range(F)]
+
+    def enqueue(s):
+        ctxs[s % F].render_frame_dev(params, [t.data_ptr() for t in dev_in[s % len(dev_in)]], img_w, img_h, outs[s % F].data_ptr(),
+                                     cubes[s % F].data_ptr() if cw else None)
+    for s in range(3 * F):
+        enqueue(s)
+    for c in ctxs:
+        c.synchronize()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(steps * F):
+        enqueue(s)
+    for c in ctxs:
+        c.synchronize()
+    dt = time.perf_counter() - t0
+    for c in ctxs:
+        c.close()
+    torch.cuda.empty_cache()
+    fps = steps * F / dt
+    r = {"preset": preset, "cubemap": bool(cubemap), "frames_in_flight": F, "steps": steps, "frames_per_s": fps,
+         "stereo_mp_per_s": fps * eq_w * eq_h / 1e6, "timing": "host clock around enqueue + synchronize of steps x F frames, inputs resident in HBM"}
+    if preset == "6k":
+        r["mono_left_eye_mp_per_s"] = fps * eq_w * (eq_h // 2) / 1e6   # BASELINE's "6K mono" = the left eye (the reference always renders both)
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,6 +453,26 @@ def main():
     stage_ms = ctxs[0].stage_ms()
     ctxs[0].set_graphs(True)
 
+    # every kernel of one frame rendered ALONE on the GPU with CUDA events around each launch (s360_profile_kernels): ms per frame,
+    # algorithmic bytes per frame (compulsory reads + writes) and the fraction of the HBM roofline that gives
+    ctxs[0].profile_enable(True)
+    n_prof_frames = 2
+    for i in range(n_prof_frames):
+        ctxs[0].render_frame_dev(params, [t.data_ptr() for t in dev_in[i % n_sets]], img_w, img_h, dev_out[0].data_ptr(), dev_cube[0].data_ptr() if cw else None)
+    kernel_table = ctxs[0].profile_kernels()
+    ctxs[0].profile_enable(False)
+
+    # the graph-replay path that `value` times and the host-pointer path that `e2e` times (and the GPU tests compare with the oracle
+    # and the reference build at this size) must give the same frame: CRC32 of frame 0 through both
+    import zlib
+    ctxs[0].render_frame_dev(params, [t.data_ptr() for t in dev_in[0]], img_w, img_h, dev_out[0].data_ptr(), dev_cube[0].data_ptr() if cw else None)
+    ctxs[0].synchronize()
+    crc_graph = zlib.crc32(dev_out[0].cpu().numpy().tobytes())
+    ctxs[0].renderStereoPanorama(params, [t.numpy() for t in pinned_in[0]], pinned_out[0].numpy(), pinned_cube[0].numpy() if cw else None)
+    crc_host = zlib.crc32(pinned_out[0].numpy().tobytes())
+    if crc_graph != crc_host:
+        raise SystemExit(f"bench: the graph-replay frame (crc {crc_graph:08x}) differs from the host-API frame (crc {crc_host:08x})")
+
     # e2e: the public host-pointer API, pinned host inputs copied in and the result copied out every step
     e2e = None
     if not args.no_e2e:
@@ -439,18 +504,38 @@ def main():
         return
 
     peak, peak_src = peaks()
+    traffic, traffic_note = ncu_traffic()
     roof = None
     if prof["launches"]:
         per_launch_s = prof["ms"] / 1000.0 / prof["launches"]
         bytes_per_launch = ALGO_BYTES_PER_LEVELPX_PER_SWEEP * prof["level_pixels"] / prof["launches"]
         achieved = bytes_per_launch / per_launch_s / 1e9
         roof = {"bound": "hbm", "kernel": "k_sweep (PixFlow wavefront sweep, forward+backward)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_SWEEP_TRAFFIC_BYTES, "traffic_note": NCU_SWEEP_TRAFFIC_NOTE,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src,
                 "avg_launch_ms": prof["ms"] / prof["launches"], "launches_timed": prof["launches"],
                 "ns_per_wavefront_step": 1e6 * prof["ms"] / max(prof["steps"], 1.0),
                 "sweep_ms_per_frame": prof["ms"] / (prof_steps * F), "sweep_generic_reruns_last_frames": prof["fallbacks"], "instrumented_pass_ms_per_step": ms_prof / prof_steps,
                 "note": "dependency-latency-bound recurrence: reported against the HBM roofline for completeness"}
+
+    roofline_all = []
+    for r in sorted(kernel_table, key=lambda r: -r["ms"]):
+        ms_f = r["ms"] / n_prof_frames
+        gb = r["algorithmic_bytes"] / n_prof_frames / 1e9
+        ach = gb / (ms_f / 1e3) if ms_f > 0 else 0.0
+        roofline_all.append({"kernel": r["kernel"], "launches_per_frame": r["launches"] / n_prof_frames, "ms_per_frame_alone": ms_f,
+                             "algorithmic_gb_per_frame": gb, "achieved_gbs": ach, "frac": ach / peak})
+
+    extra = None
+    if not args.no_extras and world == 1 and args.preset == "8k" and not args.cubemap:
+        # BASELINE configs 2 and 5 at HEAD, a few steps each: release the 8K contexts first (HBM)
+        for c in ctxs:
+            c.close()
+        ctxs.clear()
+        torch.cuda.empty_cache()
+        extra = {}
+        for name, preset, cube in (("config2_6k_mono", "6k", False), ("config5_8k_cubemap", "8k", True)):
+            extra[name] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cube, min(F, 12), steps=2)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -467,7 +552,9 @@ def main():
         "dtype": "u8/f32", "data": "synthetic",
         "config": workload_config(args.preset, args.cubemap, F, world),
         "mp_per_s": value * eq_w * eq_h / 1e6,
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_baseline,
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "roofline_all": roofline_all, "cpu_baseline": cpu_baseline,
+        "output_crc32": {"graph_replay_frame0": f"{crc_graph:08x}", "host_api_frame0": f"{crc_host:08x}", "equal": True},
+        "extra": extra,
         "stage_ms_single_frame": stage_ms, "host_enqueue_ms_per_frame": 1000.0 * t_enq / (args.steps * F),
     }
     print(json.dumps(line), flush=True)

@@ -121,6 +121,10 @@ int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, 
 /* sweep launches (since s360_profile_enable) that the generic kernel had to repeat because an operand left the range of the
  * fast kernel's written-out div/sqrt sequences; valid after s360_profile_sweep */
 int s360_profile_sweep_fallbacks(s360_ctx* ctx, unsigned long long* fallbacks);
+/* Per-kernel table of everything launched by s360_render_frame[_dev] since s360_profile_enable(ctx, 1): a JSON array of
+ * {"kernel", "ms" (CUDA events on the launching stream, summed), "algorithmic_bytes" (compulsory reads + writes of those launches),
+ * "launches"}. Synchronises the stream. *needed receives the size of the text incl. the terminator; json may be NULL to query it. */
+int s360_profile_kernels(s360_ctx* ctx, char* json, size_t cap, size_t* needed);
 
 /* ---- rig (RIG_JSON.md format) ---- */
 int s360_rig_load_file(s360_ctx* ctx, const char* json_path);

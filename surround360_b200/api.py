@@ -322,6 +322,15 @@ class Context:
         _check(lib().s360_profile_sweep_fallbacks(self.h, C.byref(fb)))
         return dict(ms=ms.value, launches=n.value, level_pixels=px.value, steps=steps.value, fallbacks=fb.value)
 
+    def profile_kernels(self):
+        """Per-kernel {kernel, ms, algorithmic_bytes, launches} since profile_enable(True)."""
+        import json
+        need = C.c_size_t()
+        _check(lib().s360_profile_kernels(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _check(lib().s360_profile_kernels(self.h, buf, need.value, C.byref(need)))
+        return json.loads(buf.value.decode())
+
     def intermediate(self, name, idx=0):
         w, h, c, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().s360_frame_intermediate(self.h, name.encode(), idx, None, C.byref(w), C.byref(h), C.byref(c), C.byref(f)))

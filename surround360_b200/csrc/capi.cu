@@ -136,6 +136,26 @@ int s360_profile_enable(s360_ctx* c, int on) {
   require(c != nullptr, "null context");
   c->profile = on != 0;
   c->sweepProfile = FlowBatch::SweepProfile();
+  c->kernelProf.clear();
+  S360_API_END
+}
+int s360_profile_kernels(s360_ctx* c, char* json, size_t cap, size_t* needed) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(c != nullptr && needed != nullptr, "null argument");
+  collectProfile(c);
+  std::string out = "[";
+  bool first = true;
+  for (const auto& kv : c->kernelProf.acc) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"ms\": %.6f, \"algorithmic_bytes\": %.0f, \"launches\": %llu}", first ? "" : ", ",
+                  kv.first.c_str(), kv.second.ms, kv.second.bytes, kv.second.launches);
+    out += buf;
+    first = false;
+  }
+  out += "]";
+  *needed = out.size() + 1;
+  if (json && cap >= out.size() + 1) std::memcpy(json, out.c_str(), out.size() + 1);
   S360_API_END
 }
 int s360_profile_sweep(s360_ctx* c, double* ms, unsigned long long* launches, double* levelPixels, double* steps) {

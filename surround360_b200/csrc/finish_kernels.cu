@@ -202,22 +202,30 @@ void launchFeatherExtend(cudaStream_t st, const uchar4* src, int w, int srcH, in
   uint8_t* a0 = scratch;
   uint8_t* a1 = scratch + plane;
   uint16_t* t = reinterpret_cast<uint16_t*>(scratch + 2 * plane);
-  k_extract_alpha<<<grid2d(w, rows, b), b, 0, st>>>(src, w, srcH, rows, flip, a0);
+  { S360_PROF(st, "k_extract_alpha", (double)plane * 5);
+    k_extract_alpha<<<grid2d(w, rows, b), b, 0, st>>>(src, w, srcH, rows, flip, a0); }
   if (erodeSize == kErR) {
     // the u16 scratch `t` (not needed before the blur) first holds the vertical minimum; a1 receives the eroded plane
     uint8_t* vtmp = reinterpret_cast<uint8_t*>(t);
-    k_erode_v31<<<dim3(iDivUp(w, 128), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, w, rows, vtmp);
-    k_erode_h31<<<dim3(iDivUp(w, kErTileW), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, vtmp, w, rows, a1);
+    { S360_PROF(st, "k_erode_v31", (double)plane * 2);
+      k_erode_v31<<<dim3(iDivUp(w, 128), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, w, rows, vtmp); }
+    { S360_PROF(st, "k_erode_h31", (double)plane * 3);
+      k_erode_h31<<<dim3(iDivUp(w, kErTileW), iDivUp(rows, kErStrip)), 128, 0, st>>>(a0, vtmp, w, rows, a1); }
     ++g_launchCount;
   } else {
-    k_erode_cross<<<grid2d(w, rows, b), b, 0, st>>>(a0, w, rows, erodeSize, a1);
+    { S360_PROF(st, "k_erode_cross", (double)plane * 2);
+      k_erode_cross<<<grid2d(w, rows, b), b, 0, st>>>(a0, w, rows, erodeSize, a1); }
   }
   if (erodeSize == kB8N) {
-    k_blur8_rows31<<<dim3(iDivUp(w, kB8TileW), iDivUp(rows, 8)), b, 0, st>>>(a1, w, rows, blurKernelFixed, t);
-    k_blur8_cols_extend31<<<dim3(iDivUp(w, 128), iDivUp(rows, kB8Strip)), 128, 0, st>>>(t, w, rows, blurKernelFixed, src, srcH, flip, extOut, extW);
+    { S360_PROF(st, "k_blur8_rows31", (double)plane * 3);
+      k_blur8_rows31<<<dim3(iDivUp(w, kB8TileW), iDivUp(rows, 8)), b, 0, st>>>(a1, w, rows, blurKernelFixed, t); }
+    { S360_PROF(st, "k_blur8_cols_extend31", (double)plane * 6 + (double)extW * rows * 4);
+      k_blur8_cols_extend31<<<dim3(iDivUp(w, 128), iDivUp(rows, kB8Strip)), 128, 0, st>>>(t, w, rows, blurKernelFixed, src, srcH, flip, extOut, extW); }
   } else {
-    k_blur8_rows<<<grid2d(w, rows, b), b, 0, st>>>(a1, w, rows, blurKernelFixed, erodeSize, t);
-    k_blur8_cols_extend<<<grid2d(w, rows, b), b, 0, st>>>(t, w, rows, blurKernelFixed, erodeSize, src, srcH, flip, extOut, extW);
+    { S360_PROF(st, "k_blur8_rows", (double)plane * 3);
+      k_blur8_rows<<<grid2d(w, rows, b), b, 0, st>>>(a1, w, rows, blurKernelFixed, erodeSize, t); }
+    { S360_PROF(st, "k_blur8_cols_extend", (double)plane * 6 + (double)extW * rows * 4);
+      k_blur8_cols_extend<<<grid2d(w, rows, b), b, 0, st>>>(t, w, rows, blurKernelFixed, erodeSize, src, srcH, flip, extOut, extW); }
   }
   g_launchCount += 4;
 }
@@ -232,7 +240,8 @@ __global__ void k_extend_wrap(const uchar4* __restrict__ src, int w, int rows, u
 }
 void launchExtendWrap(cudaStream_t st, const uchar4* src, int w, int rows, uchar4* extOut, int extW) {
   dim3 b(32, 8);
-  k_extend_wrap<<<grid2d(extW, rows, b), b, 0, st>>>(src, w, rows, extOut, extW);
+  { S360_PROF(st, "k_extend_wrap", ((double)w + extW) * rows * 4);
+    k_extend_wrap<<<grid2d(extW, rows, b), b, 0, st>>>(src, w, rows, extOut, extW); }
   ++g_launchCount;
 }
 
@@ -256,7 +265,8 @@ __global__ void k_pr_prepare(const uint8_t* __restrict__ src, const uint8_t* __r
 }
 void launchPoleRemovalPrepare(cudaStream_t st, const uint8_t* srcBGR, const uint8_t* maskBGR, int w, int h, float radius, uchar4* dst) {
   dim3 b(32, 8);
-  k_pr_prepare<<<grid2d(w, h, b), b, 0, st>>>(srcBGR, maskBGR, w, h, radius, dst);
+  { S360_PROF(st, "k_pr_prepare", (double)w * h * 10);
+    k_pr_prepare<<<grid2d(w, h, b), b, 0, st>>>(srcBGR, maskBGR, w, h, radius, dst); }
   ++g_launchCount;
 }
 __global__ void k_flip_both(const uchar4* __restrict__ src, int w, int h, uchar4* __restrict__ dst) {
@@ -266,7 +276,8 @@ __global__ void k_flip_both(const uchar4* __restrict__ src, int w, int h, uchar4
 }
 void launchFlipBoth(cudaStream_t st, const uchar4* src, int w, int h, uchar4* dst) {
   dim3 b(32, 8);
-  k_flip_both<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, dst);
+  { S360_PROF(st, "k_flip_both", (double)w * h * 8);
+    k_flip_both<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, dst); }
   ++g_launchCount;
 }
 __global__ void __launch_bounds__(256)
@@ -291,7 +302,8 @@ k_pr_merge(const uchar4* __restrict__ img1, const uchar4* __restrict__ img2, con
 void launchPoleRemovalMerge(cudaStream_t st, const uchar4* img1, const uchar4* img2, const float2* flow, int w, int h, float radius,
                             uchar4* dst, const RemapTables& rt) {
   dim3 b(32, 8);
-  k_pr_merge<<<grid2d(w, h, b), b, 0, st>>>(img1, img2, flow, w, h, radius, dst, rt.wi);
+  { S360_PROF(st, "k_pr_merge", (double)w * h * 20);
+    k_pr_merge<<<grid2d(w, h, b), b, 0, st>>>(img1, img2, flow, w, h, radius, dst, rt.wi); }
   ++g_launchCount;
 }
 
@@ -317,7 +329,8 @@ __global__ void k_flatten(const uchar4* __restrict__ base, const uchar4* __restr
 }
 void launchFlatten(cudaStream_t st, const uchar4* base, const uchar4* top, int w, int h, uchar4* out, const RemapTables& rt) {
   const size_t n = (size_t)w * h;
-  k_flatten<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(base, top, n, out, rt);
+  { S360_PROF(st, "k_flatten", (double)n * 12);
+    k_flatten<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(base, top, n, out, rt); }
   ++g_launchCount;
 }
 // TRSP:864-885: sph = flatten(sph, topWarped); sph = flip(flatten(flip(sph), bottomWarped)).
@@ -339,7 +352,8 @@ k_flatten_poles(const uchar4* __restrict__ base, int w, int h, const uchar4* __r
 void launchFlattenPoles(cudaStream_t st, const uchar4* base, int w, int h, const uchar4* topLayer, const uchar4* botLayer,
                         int poleRows, uchar4* out, const RemapTables& rt) {
   dim3 b(32, 8);
-  k_flatten_poles<<<grid2d(w, h, b), b, 0, st>>>(base, w, h, topLayer, botLayer, poleRows, out, rt);
+  { S360_PROF(st, "k_flatten_poles", (double)w * h * 8 + (double)w * poleRows * 4 * ((topLayer ? 1 : 0) + (botLayer ? 1 : 0)));
+    k_flatten_poles<<<grid2d(w, h, b), b, 0, st>>>(base, w, h, topLayer, botLayer, poleRows, out, rt); }
   ++g_launchCount;
 }
 
@@ -443,12 +457,19 @@ void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, int eyes, float a
   uchar4* tB = scratchLp + (size_t)eyes * w * h;
   const float alpha = powf(0.25f, 1.0f / 4.0f);
   dim3 tb(32, 8);
-  k_transpose4<<<dim3(iDivUp(w, 32), iDivUp(h, 32), eyes), tb, 0, st>>>(img, w, h, tA);                 // tA: h wide, w tall
-  k_iir_columns<true><<<dim3(iDivUp(h, 128), eyes), 128, 0, st>>>(tA, h, w, alpha, scratchF, tB);       // horizontal pass (wrap)
-  k_transpose4<<<dim3(iDivUp(h, 32), iDivUp(w, 32), eyes), tb, 0, st>>>(tB, h, w, tA);                 // tA: w wide, h tall
-  k_iir_columns<false><<<dim3(iDivUp(w, 128), eyes), 128, 0, st>>>(tA, w, h, alpha, scratchF, tB);      // vertical pass (reflect)
   const size_t n = (size_t)eyes * w * h;
-  k_unsharp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, tB, n, amount);
+  // algorithmic bytes: the reference's images are 3-channel (sharpen: 7 planes x 3 B per pixel in all); the transposes
+  // exist only because the recurrence runs along columns here
+  { S360_PROF(st, "k_transpose4", (double)n * 8);
+    k_transpose4<<<dim3(iDivUp(w, 32), iDivUp(h, 32), eyes), tb, 0, st>>>(img, w, h, tA); }                 // tA: h wide, w tall
+  { S360_PROF(st, "k_iir_columns", (double)n * 6);
+    k_iir_columns<true><<<dim3(iDivUp(h, 128), eyes), 128, 0, st>>>(tA, h, w, alpha, scratchF, tB); }       // horizontal pass (wrap)
+  { S360_PROF(st, "k_transpose4", (double)n * 8);
+    k_transpose4<<<dim3(iDivUp(h, 32), iDivUp(w, 32), eyes), tb, 0, st>>>(tB, h, w, tA); }                 // tA: w wide, h tall
+  { S360_PROF(st, "k_iir_columns", (double)n * 6);
+    k_iir_columns<false><<<dim3(iDivUp(w, 128), eyes), 128, 0, st>>>(tA, w, h, alpha, scratchF, tB); }      // vertical pass (reflect)
+  { S360_PROF(st, "k_unsharp", (double)n * 9);
+    k_unsharp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, tB, n, amount); }
   g_launchCount += 5;
 }
 

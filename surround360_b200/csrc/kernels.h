@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <map>
+#include <string>
 #include <vector>
 #include "common.cuh"
 #include "remap.cuh"
@@ -125,6 +127,37 @@ struct FlowPrevPtrs {  // optional temporal inputs
   int prevPitch[kMaxFlowBatch];
   bool enabled = false;
 };
+
+
+// ------------------------------------------------------------------------------------
+// Per-kernel profiling (bench.py's `roofline_all`): when a context enables it, every launch of the frame is bracketed by two
+// CUDA events on the launching stream and tagged with the kernel's name and its ALGORITHMIC bytes (compulsory reads + writes
+// of that launch). Off by default: the scope object is two pointer tests.
+// ------------------------------------------------------------------------------------
+struct KernelProf {
+  struct Rec { const char* name; double bytes; cudaEvent_t a, b; };
+  struct Acc { double ms = 0, bytes = 0; unsigned long long launches = 0; };
+  bool on = false;
+  std::vector<Rec> pending;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, Acc> acc;
+  cudaEvent_t get();
+  void collect();   // after the stream has been synchronised
+  void clear();
+  ~KernelProf();
+};
+extern thread_local KernelProf* t_kernelProf;   // set by the pipeline for the duration of a frame's launches
+struct ProfScope {
+  cudaStream_t st;
+  KernelProf::Rec rec;
+  bool on;
+  ProfScope(cudaStream_t s, const char* name, double bytes);
+  ~ProfScope();
+};
+#define S360_PROF_CAT2(a, b) a##b
+#define S360_PROF_CAT(a, b) S360_PROF_CAT2(a, b)
+// usage: { S360_PROF(st, "k_name", bytes); k_name<<<...>>>(...); }
+#define S360_PROF(st, name, bytes) ::s360::ProfScope S360_PROF_CAT(_prof_, __LINE__)(st, name, (double)(bytes))
 
 class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved concurrently
  public:

@@ -524,7 +524,15 @@ static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
   uint8_t* cube = wantCube ? F.outCube.as<uint8_t>() : nullptr;
   const bool useGraph = c->useGraphs && !c->profile && !c->keepIntermediates;
   if (!useGraph) {
-    enqueueFrame(c, dev.data(), F.outEq.as<uint8_t>(), cube, true);
+    c->kernelProf.on = c->profile;
+    t_kernelProf = c->profile ? &c->kernelProf : nullptr;   // launches of this frame are made by this thread
+    try {
+      enqueueFrame(c, dev.data(), F.outEq.as<uint8_t>(), cube, true);
+    } catch (...) {
+      t_kernelProf = nullptr;
+      throw;
+    }
+    t_kernelProf = nullptr;
     F.lastWasTimed = true;
     if (F.temporal) F.prevValid = true;
     return;
@@ -776,6 +784,7 @@ void collectProfile(s360_ctx* c) {
   S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   if (c->plan->sideFlow) c->plan->sideFlow->collectProfile(&c->sweepProfile);
   if (c->plan->poleFlowBatch) c->plan->poleFlowBatch->collectProfile(&c->sweepProfile);
+  c->kernelProf.collect();
 }
 }
 s360_ctx::s360_ctx() {}

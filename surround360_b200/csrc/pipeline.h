@@ -55,6 +55,7 @@ struct s360_ctx {
   bool useGraphs = true;
   bool temporal = false;
   s360::FlowBatch::SweepProfile sweepProfile;
+  s360::KernelProf kernelProf;          // per-kernel CUDA-event times + algorithmic bytes while `profile` is on
   float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   std::string idScratch;
 

@@ -10,6 +10,41 @@ namespace s360 {
 
 std::atomic<unsigned long long> g_launchCount{0};
 
+// ---- per-kernel profiling (kernels.h) ----
+thread_local KernelProf* t_kernelProf = nullptr;
+cudaEvent_t KernelProf::get() {
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e;
+  S360_CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+void KernelProf::collect() {
+  for (auto& r : pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      Acc& a = acc[r.name];
+      a.ms += ms; a.bytes += r.bytes; a.launches += 1;
+    }
+    pool.push_back(r.a); pool.push_back(r.b);
+  }
+  pending.clear();
+}
+void KernelProf::clear() { acc.clear(); }
+KernelProf::~KernelProf() {
+  for (auto& r : pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : pool) cudaEventDestroy(e);
+}
+ProfScope::ProfScope(cudaStream_t s, const char* name, double bytes) : st(s), on(t_kernelProf && t_kernelProf->on) {
+  if (!on) return;
+  rec.name = name; rec.bytes = bytes; rec.a = t_kernelProf->get(); rec.b = t_kernelProf->get();
+  cudaEventRecord(rec.a, st);
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  cudaEventRecord(rec.b, st);
+  t_kernelProf->pending.push_back(rec);
+}
+
 static inline dim3 grid2d(int w, int h, dim3 b) { return dim3(iDivUp(w, b.x), iDivUp(h, b.y)); }
 
 // ------------------------------------------------------------------------------------
@@ -31,6 +66,7 @@ __global__ void k_prep_source(const uint8_t* __restrict__ src, int cn, int w, in
 }
 void launchPrepSource(cudaStream_t st, const uint8_t* src, int cn, int w, int h, int feather, uchar4* dst) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_prep_source", (double)w * h * (cn + 4));
   k_prep_source<<<grid2d(w, h, b), b, 0, st>>>(src, cn, w, h, feather, dst);
   ++g_launchCount;
 }
@@ -43,6 +79,7 @@ __global__ void k_unpack_bgra(const uint8_t* __restrict__ src, int cn, size_t n,
 }
 void launchUnpackBGRA(cudaStream_t st, const uint8_t* src, int cn, int w, int h, uchar4* dst) {
   const size_t n = (size_t)w * h;
+  S360_PROF(st, "k_unpack_bgra", (double)n * (cn + 4));
   k_unpack_bgra<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, cn, n, dst);
   ++g_launchCount;
 }
@@ -55,6 +92,7 @@ __global__ void k_pack_bgr(const uchar4* __restrict__ src, int w, int h, int pit
 }
 void launchPackBGR(cudaStream_t st, const uchar4* src, int w, int h, int pitch, uint8_t* dst) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_pack_bgr", (double)w * h * 7);
   k_pack_bgr<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, pitch, dst);
   ++g_launchCount;
 }
@@ -65,6 +103,7 @@ __global__ void k_pack_bgra(const uchar4* __restrict__ src, int w, int h, int pi
 }
 void launchPackBGRA(cudaStream_t st, const uchar4* src, int w, int h, int pitch, uint8_t* dst) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_pack_bgra", (double)w * h * 8);
   k_pack_bgra<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, pitch, reinterpret_cast<uchar4*>(dst));
   ++g_launchCount;
 }
@@ -98,6 +137,7 @@ void launchProjectSpherical(cudaStream_t st, const uchar4* src, int sw, int sh, 
                             uchar4* dst, int dw, int dh, int dstPitch, int poleMode, int featherStart, int featherSize,
                             const RemapTables& rt) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_project_spherical", ((double)sw * sh + (double)dw * dh) * 4);   // the source once + the projection written
   k_project_spherical<<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, cam, tb, dst, dw, dh, dstPitch, poleMode, featherStart,
                                                          featherSize, rt.wi);
   ++g_launchCount;
@@ -191,6 +231,8 @@ __global__ void __launch_bounds__(256) k_novel_view(NovelViewArgs a, RemapTables
 }
 void launchNovelView(cudaStream_t st, const NovelViewArgs& a, const RemapTables& rt) {
   dim3 b(32, 8);
+  // per pair: two overlap images (4 B) and two flows (8 B) in; both eyes' panorama strips out
+  S360_PROF(st, "k_novel_view", (double)a.numCams * a.overlapW * a.camH * (2 * 4 + 2 * 8) + 2.0 * a.eqrW * a.camH * 4);
   k_novel_view<<<grid2d(a.eqrW, a.camH, b), b, 0, st>>>(a, rt);
   ++g_launchCount;
 }
@@ -207,6 +249,7 @@ void launchNovelViewChunk(cudaStream_t st, const uchar4* ovL, const uchar4* ovR,
                           int w, int h, int bufW, int camW, int numNovel, float slabDisp, uchar4* chunkL, uchar4* chunkR,
                           const RemapTables& rt) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_novel_chunk", (double)w * h * 24 + 2.0 * bufW * h * 4);
   k_novel_chunk<<<grid2d(bufW, h, b), b, 0, st>>>(ovL, ovR, pitch, flowLR, flowRL, w, h, bufW, camW, numNovel, slabDisp, chunkL,
                                                    chunkR, rt);
   ++g_launchCount;
@@ -219,6 +262,7 @@ __global__ void k_offset_wrap(const uchar4* __restrict__ src, int w, int h, floa
 }
 void launchOffsetWrap(cudaStream_t st, const uchar4* src, int w, int h, float offset, uchar4* dst) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_offset_wrap", (double)w * h * 8);
   k_offset_wrap<<<grid2d(w, h, b), b, 0, st>>>(src, w, h, offset, dst);
   ++g_launchCount;
 }
@@ -252,6 +296,7 @@ __global__ void __launch_bounds__(256) k_pole_warp(PoleWarpArgs a, const short* 
 }
 void launchPoleWarp(cudaStream_t st, const PoleWarpArgs& a, const RemapTables& rt) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_pole_warp", (double)a.extW * a.rows * (8 + 4) + (double)a.cols * a.rows * 4);
   k_pole_warp<<<grid2d(a.cols, a.rows, b), b, 0, st>>>(a, rt.wi);
   ++g_launchCount;
 }
@@ -323,6 +368,7 @@ k_resize_cubic8(const uchar4* __restrict__ src, int sw, int sh, int spitch, ucha
 void launchResizeCubic8(cudaStream_t st, const uchar4* src, int sw, int sh, int spitch, int cn, uchar4* dst, int dw, int dh, int dpitch,
                         uint8_t* dstPacked3) {
   dim3 b(32, 8);
+  S360_PROF(st, "k_resize_cubic8", (double)sw * sh * 4 + (double)dw * dh * (dstPacked3 ? 3 : 4));
   if (cn == 4) k_resize_cubic8<4><<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, dstPacked3, resizeScale(sw, dw),
                                                                 resizeScale(sh, dh));
   else k_resize_cubic8<3><<<grid2d(dw, dh, b), b, 0, st>>>(src, sw, sh, spitch, dst, dw, dh, dpitch, dstPacked3, resizeScale(sw, dw),
@@ -422,6 +468,7 @@ void launchCubemap(cudaStream_t st, const uchar4* eye, int w, int h, int faceW, 
                    const RemapTables& rt) {
   dim3 b(32, 8);
   dim3 g(iDivUp(faceW, 32), iDivUp(faceH, 8), 6);
+  S360_PROF(st, "k_cubemap", (double)w * h * 4 + 6.0 * faceW * faceH * 3);
   k_cubemap<<<g, b, 0, st>>>(eye, w, h, faceW, faceH, photo, outPacked3, rt.wi);
   ++g_launchCount;
 }

@@ -3,7 +3,14 @@
 // before GPU time is spent on it. Not part of the package, the C ABI, the tests or bench.py.
 #include "../../surround360_b200/csrc/kernels.h"
 
-namespace s360 { std::atomic<unsigned long long> g_launchCount{0}; }
+namespace s360 {
+std::atomic<unsigned long long> g_launchCount{0};
+// the flow-only emulation library has no warp_kernels.cu: the kernel profiler is off
+thread_local KernelProf* t_kernelProf = nullptr;
+ProfScope::ProfScope(cudaStream_t s, const char*, double) : st(s), on(false) {}
+ProfScope::~ProfScope() {}
+KernelProf::~KernelProf() {}
+}
 
 extern "C" int emu_flow_batch(const char* alg, int n, const uint8_t* const* i0, const uint8_t* const* i1, const int* hints, int w, int h,
                               float* flowOut /* [n][h][w][2] */) {

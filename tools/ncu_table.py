@@ -21,7 +21,7 @@ def hbm_peak():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            for k in ("hbm_gbps", "hbm_GBps", "hbm_copy_gbps", "hbm"):
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_GBps", "hbm_copy_gbps", "hbm"):
                 if k in d:
                     v = d[k]
                     return float(v["burst"] if isinstance(v, dict) and "burst" in v else v)
@@ -89,9 +89,66 @@ def launch_table(path):
     print(f"| total | {sum(v[0] for v in agg.values())} | {tot:.3f} | |")
 
 
+def counters_table(path, frames=1.0):
+    """Per-kernel table from a `--metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_*` pass over a frame
+    (`--csv --log-file`): time, warp instructions, DRAM traffic, share of the frame's instruction budget."""
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr, rows = rows[0], rows[1:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r[ix["ID"]], {"name": re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("void ", "").strip()})
+        d[r[ix["Metric Name"]]] = num(r[ix["Metric Value"]])
+    agg = collections.defaultdict(lambda: collections.defaultdict(float))
+    for d in per.values():
+        a = agg[re.sub(r"<.*", "", d["name"])]
+        a["n"] += 1
+        a["ms"] += d.get("gpu__time_duration.sum", 0) / 1e6
+        a["inst"] += d.get("smsp__inst_executed.sum", 0)
+        a["dram"] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+        a["issue_w"] += d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0) * d.get("gpu__time_duration.sum", 0)
+    tot_ms = sum(a["ms"] for a in agg.values()); tot_i = sum(a["inst"] for a in agg.values())
+    peak = hbm_peak()
+    print(f"{len(per)} launches = {frames:.2f} frame(s): {tot_ms / frames:.1f} ms and {tot_i / frames / 1e9:.2f} G warp instructions per frame alone; "
+          f"at 148 SMs x 4 issue slots x 1.965 GHz = 1163 G/s the instructions alone need {tot_i / frames / 1163e9 * 1e3:.1f} ms per frame\n")
+    print("| kernel | launches | ms | G warp-inst | % of inst | issue active % | DRAM GB | GB/s | % of HBM peak |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["inst"]):
+        print(f"| {k} | {int(a['n'])} | {a['ms']:.2f} | {a['inst'] / 1e9:.3f} | {100 * a['inst'] / tot_i:.1f} | {a['issue_w'] / max(a['ms'] * 1e6, 1):.0f} | "
+              f"{a['dram'] / 1e9:.2f} | {a['dram'] / 1e9 / max(a['ms'] / 1e3, 1e-9):.0f} | {100 * a['dram'] / 1e9 / max(a['ms'] / 1e3, 1e-9) / peak:.0f} |")
+
+
+def traffic_json(path, kernel_regex, out):
+    """dram bytes per launch of the launches whose name matches, from a raw `--set full` export -> JSON for bench.py."""
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    vals = []
+    for r in rows[2:]:
+        if len(r) < len(hdr) or not re.search(kernel_regex, r[col["Kernel Name"]]):
+            continue
+        b = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += num(r[col[name]]) * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(units[col[name]].lower(), 1)
+        vals.append(b)
+    j = {"kernel_regex": kernel_regex, "source": os.path.relpath(path, ROOT), "launches": len(vals), "dram_bytes_per_launch": sum(vals) / max(len(vals), 1),
+         "note": f"mean dram__bytes_read.sum + dram__bytes_write.sum of {len(vals)} captured launch(es) ({os.path.basename(path)}, ncu --set full)"}
+    json.dump(j, open(out, "w"), indent=1)
+    print(json.dumps(j))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("csv")
     ap.add_argument("--launches", action="store_true")
+    ap.add_argument("--counters", action="store_true", help="per-kernel time / instructions / DRAM table from a --metrics pass")
+    ap.add_argument("--frames", type=float, default=1.0, help="frames covered by the --counters capture")
+    ap.add_argument("--traffic", metavar="KERNEL_REGEX", help="write the dominant kernel's DRAM bytes per launch as JSON (--out)")
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_dominant_kernel_traffic.json"))
     a = ap.parse_args()
-    (launch_table if a.launches else raw_table)(a.csv)
+    if a.traffic:
+        traffic_json(a.csv, a.traffic, a.out)
+    elif a.counters:
+        counters_table(a.csv, a.frames)
+    else:
+        (launch_table if a.launches else raw_table)(a.csv)
