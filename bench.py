@@ -250,13 +250,16 @@ def workload_config(preset, cubemap, frames_per_step, world):
             "parallelism": f"frames sharded one-per-GPU x{world}, single NCCL broadcast of the rig"}
 
 
-def side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cubemap, F, steps):
-    """A short device-resident throughput pass of another BASELINE config (frames in flight = F)."""
+def side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cubemap, F, steps, temporal=False):
+    """A short device-resident throughput pass of another configuration (frames in flight = F). temporal: video mode -- every context is
+    a chain whose frame i regularises against its frame i-1 (--prev_frame_data_dir, kept on the device: s360_ctx_set_temporal)."""
     params = api.default_params(**preset_kwargs(preset, cubemap))
     ctxs = []
     for _ in range(F):
         c = api.Context(local_rank)
         c.load_rig_blob(blob_host)
+        if temporal:
+            c.set_temporal(True)
         ctxs.append(c)
     eq_w, eq_h, cw, ch = ctxs[0].output_size(params)
     img_h, img_w = frame_sets[0][0].shape[:2]
@@ -286,6 +289,9 @@ def side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cubema
          "stereo_mp_per_s": fps * eq_w * eq_h / 1e6, "timing": "host clock around enqueue + synchronize of steps x F frames, inputs resident in HBM"}
     if preset == "6k":
         r["mono_left_eye_mp_per_s"] = fps * eq_w * (eq_h // 2) / 1e6   # BASELINE's "6K mono" = the left eye (the reference always renders both)
+    if temporal:
+        r["video_mode"] = "every context is one chain of consecutive frames (temporal regularisation against the previous frame, on the device)"
+        r["chains_in_flight"] = F
     return r
 
 
@@ -300,6 +306,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=20, help="frames in flight per GPU (contexts/streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--temporal", action="store_true", help="video mode: every context is a chain (frame i regularises against frame i-1 of its context)")
     ap.add_argument("--no-extras", action="store_true", help="skip the short 6k / cubemap passes appended to the headline line")
     ap.add_argument("--cpu-arm-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--worker-kind", default="reference", help=argparse.SUPPRESS)
@@ -333,6 +340,8 @@ def main():
 
     F = max(1, args.inflight)
     ctxs = [api.Context(local_rank)]
+    if args.temporal:
+        ctxs[0].set_temporal(True)
     # rig: parsed on rank 0, one NCCL broadcast of the serialised tables, every rank deserialises
     rig_path = f"/tmp/s360_bench_rig_{rank}.json"
     rig_gen.write_rig(rig_path)
@@ -368,6 +377,9 @@ def main():
         c = api.Context(local_rank)
         c.load_rig_blob(blob_host)
         ctxs.append(c)
+    if args.temporal:
+        for c in ctxs[1:]:
+            c.set_temporal(True)
     img_h, img_w = frame_sets[0][0].shape[:2]
     n_cam = len(frame_sets[0])
     h2d_bytes = n_cam * img_w * img_h * 3
@@ -536,6 +548,9 @@ def main():
         extra = {}
         for name, preset, cube in (("config2_6k_mono", "6k", False), ("config5_8k_cubemap", "8k", True)):
             extra[name] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cube, min(F, 12), steps=2)
+        # video mode (SURVEY 8e option A: contiguous frame ranges, one chain per context): many chains in flight, and one chain alone
+        extra["video_8k_chains"] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, "8k", False, min(F, 12), steps=2, temporal=True)
+        extra["video_8k_single_chain"] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, "8k", False, 1, steps=4, temporal=True)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -550,7 +565,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32", "data": "synthetic",
-        "config": workload_config(args.preset, args.cubemap, F, world),
+        "config": dict(workload_config(args.preset, args.cubemap, F, world), **({"video_mode": "temporal chains, one per context"} if args.temporal else {})),
         "mp_per_s": value * eq_w * eq_h / 1e6,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "roofline_all": roofline_all, "cpu_baseline": cpu_baseline,
         "output_crc32": {"graph_replay_frame0": f"{crc_graph:08x}", "host_api_frame0": f"{crc_host:08x}", "equal": True},

@@ -23,7 +23,7 @@
  *                             source/render/RigDescription.cpp:18-78)
  *
  * Conventions: plain pointers and sizes; images are tightly packed row-major unless a
- * stride is given; BGRA8 / BGR8 / float2 flow exactly as the reference's cv::Mat types
+ * stride is given (the *_strided variants); BGRA8 / BGR8 / float2 flow exactly as the reference's cv::Mat types
  * (CV_8UC4 / CV_8UC3 / CV_32FC2). Every function returns 0 on success, non-zero on error
  * (no exceptions cross the ABI); s360_last_error() returns the message for the calling
  * thread. A context is bound to one CUDA device and must not be shared between host
@@ -174,11 +174,32 @@ int s360_flow_compute(s360_ctx* ctx, const char* alg_name, const uint8_t* i0_bgr
 int s360_flow_compute_batch(s360_ctx* ctx, const char* alg_name, int n, const uint8_t* const* i0_bgra,
                             const uint8_t* const* i1_bgra, int w, int h, float* const* flow_out, const s360_hint* hints);
 
+/* Stride-aware variant for non-contiguous cv::Mat views (the reference's overlap images are ROI crops, TRSP:196-198): every
+ * *_stride is the distance between rows in BYTES (0 = tightly packed). prev_i0 is not needed (the reference resizes it and never
+ * reads it, PixFlow.h:106). */
+int s360_flow_compute_strided(s360_ctx* ctx, const char* alg_name, const uint8_t* i0_bgra, size_t i0_stride, const uint8_t* i1_bgra,
+                              size_t i1_stride, int w, int h, const float* prev_flow, size_t prev_flow_stride, const uint8_t* prev_i1_bgra,
+                              size_t prev_i1_stride, float* flow_out, size_t flow_out_stride, s360_hint hint);
+/* Device-pointer variant: BGRA8 images resident in HBM (row strides in bytes, multiples of 4; 0 = packed), flow written densely
+ * (w*h float2) to flow_out_dev. Enqueued on the context stream without synchronising; the solver for (algorithm, size) is
+ * created on first use and kept by the context. */
+int s360_flow_compute_dev(s360_ctx* ctx, const char* alg_name, const uint8_t* i0_bgra_dev, size_t i0_stride, const uint8_t* i1_bgra_dev,
+                          size_t i1_stride, int w, int h, float* flow_out_dev, s360_hint hint);
+
 /* NovelViewGeneratorLazyFlow::combineLazyNovelViews for one camera pair with the warp buffer
  * of renderStereoPanoramaChunksThread (TRSP:259-292). Outputs two BGRA8 chunks buf_w x h. */
 int s360_novel_view_chunk(s360_ctx* ctx, const uint8_t* overlap_l, const uint8_t* overlap_r, const float* flow_l_to_r,
                           const float* flow_r_to_l, int w, int h, int buf_w, int cam_w, int num_novel, float slab_disp,
                           uint8_t* chunk_l, uint8_t* chunk_r);
+
+/* Device-pointer variant (overlap images share one row stride in bytes, 0 = packed; flows and chunks dense); no synchronisation. */
+int s360_novel_view_chunk_dev(s360_ctx* ctx, const uint8_t* overlap_l_dev, const uint8_t* overlap_r_dev, size_t overlap_stride,
+                              const float* flow_l_to_r_dev, const float* flow_r_to_l_dev, int w, int h, int buf_w, int cam_w, int num_novel,
+                              float slab_disp, uint8_t* chunk_l_dev, uint8_t* chunk_r_dev);
+/* s360_project_spherical with row strides in bytes for source and destination (0 = packed) */
+int s360_project_spherical_strided(s360_ctx* ctx, int cam, const uint8_t* src, size_t src_stride, int src_w, int src_h, int src_channels,
+                                   float left_angle, float right_angle, float top_angle, float bottom_angle, int feather,
+                                   uint8_t* dst_bgra, size_t dst_stride, int dst_w, int dst_h);
 
 int s360_flatten_deghost(s360_ctx* ctx, const uint8_t* base_bgra, const uint8_t* top_bgra, int w, int h, uint8_t* out_bgra);
 int s360_feather_alpha(s360_ctx* ctx, const uint8_t* src_bgra, int w, int h, int erode_size, uint8_t* out_bgra);

@@ -168,6 +168,33 @@ class Context:
                                        _p(p0) if p0 is not None else None, _p(p1) if p1 is not None else None, _p(flow), int(hint)))
         return flow
 
+    def computeOpticalFlowStrided(self, alg_name, I0view, I1view, prevFlow=None, prevI1BGRA=None, hint=DirectionHint.UNKNOWN):
+        """computeOpticalFlow on non-contiguous views (numpy slices of wider images, like the reference's ROI crops, TRSP:196-198):
+        the row strides go through the ABI, nothing is copied on the host."""
+        for a in (I0view, I1view):
+            assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 4 and a.strides[1] == 4 and a.strides[2] == 1
+        h, w = I0view.shape[:2]
+        flow = np.zeros((h, w, 2), np.float32)
+        pf = p1 = None
+        if prevFlow is not None:
+            pf, p1 = prevFlow, prevI1BGRA
+        _check(lib().s360_flow_compute_strided(self.h, alg_name.encode(), C.c_void_p(I0view.ctypes.data), C.c_size_t(I0view.strides[0]),
+                                               C.c_void_p(I1view.ctypes.data), C.c_size_t(I1view.strides[0]), w, h,
+                                               C.c_void_p(pf.ctypes.data) if pf is not None else None, C.c_size_t(pf.strides[0] if pf is not None else 0),
+                                               C.c_void_p(p1.ctypes.data) if p1 is not None else None, C.c_size_t(p1.strides[0] if p1 is not None else 0),
+                                               _p(flow), C.c_size_t(0), int(hint)))
+        return flow
+
+    def flow_compute_dev(self, alg_name, i0_ptr, i0_stride, i1_ptr, i1_stride, w, h, flow_ptr, hint=DirectionHint.UNKNOWN):
+        """Device pointers (ints), strides in bytes; enqueues on the context stream, no synchronisation."""
+        _check(lib().s360_flow_compute_dev(self.h, alg_name.encode(), C.c_void_p(int(i0_ptr)), C.c_size_t(i0_stride), C.c_void_p(int(i1_ptr)),
+                                           C.c_size_t(i1_stride), w, h, C.c_void_p(int(flow_ptr)), int(hint)))
+
+    def novel_view_chunk_dev(self, ovl_ptr, ovr_ptr, ov_stride, flr_ptr, frl_ptr, w, h, buf_w, cam_w, num_novel, slab_disp, out_l_ptr, out_r_ptr):
+        _check(lib().s360_novel_view_chunk_dev(self.h, C.c_void_p(int(ovl_ptr)), C.c_void_p(int(ovr_ptr)), C.c_size_t(ov_stride), C.c_void_p(int(flr_ptr)),
+                                               C.c_void_p(int(frl_ptr)), w, h, buf_w, cam_w, num_novel, C.c_float(slab_disp),
+                                               C.c_void_p(int(out_l_ptr)), C.c_void_p(int(out_r_ptr))))
+
     def computeOpticalFlowBatch(self, alg_name, I0s, I1s, hints):
         i0 = [_c(a, np.uint8) for a in I0s]
         i1 = [_c(a, np.uint8) for a in I1s]

@@ -351,6 +351,91 @@ int s360_flow_compute(s360_ctx* c, const char* alg, const uint8_t* i0, const uin
   S360_API_END
 }
 
+// ---- stride-aware and device-pointer variants (cv::Mat views are not contiguous; the reference crops its overlap
+// images as ROI views, TRSP:196-198) ----
+static void copyIn2D(void* dst, size_t dstRowBytes, const void* src, size_t srcStrideBytes, size_t rowBytes, int rows, cudaStream_t st) {
+  S360_CUDA_CHECK(cudaMemcpy2DAsync(dst, dstRowBytes, src, srcStrideBytes ? srcStrideBytes : rowBytes, rowBytes, rows, cudaMemcpyHostToDevice, st));
+}
+int s360_flow_compute_strided(s360_ctx* c, const char* alg, const uint8_t* i0, size_t i0Stride, const uint8_t* i1, size_t i1Stride, int w, int h,
+                              const float* prevFlow, size_t prevFlowStride, const uint8_t* prevI1, size_t prevI1Stride, float* flowOut,
+                              size_t flowOutStride, s360_hint hint) {
+  S360_API_BEGIN
+  useDevice(c);
+  FlowParams fp;
+  if (!flowParamsByName(alg, &fp)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + (alg ? alg : "(null)"));
+  require(w > 0 && h > 0 && i0 && i1 && flowOut, "bad flow arguments");
+  const size_t rowB = (size_t)w * 4, rowF = (size_t)w * 8;
+  require((!i0Stride || i0Stride >= rowB) && (!i1Stride || i1Stride >= rowB) && (!flowOutStride || flowOutStride >= rowF), "stride smaller than a row");
+  cudaStream_t st = c->stream;
+  const size_t px = (size_t)w * h;
+  DeviceBuffer d0(px * 4), d1(px * 4), dF(px * 8), dPF, dP1;
+  copyIn2D(d0.p, rowB, i0, i0Stride, rowB, h, st);
+  copyIn2D(d1.p, rowB, i1, i1Stride, rowB, h, st);
+  FlowImagePtrs ip{};
+  FlowPrevPtrs pv{};
+  ip.i0[0] = d0.as<uchar4>(); ip.i1[0] = d1.as<uchar4>(); ip.pitch0[0] = ip.pitch1[0] = w; ip.hint[0] = (int)hint;
+  if (prevFlow) {
+    require(prevI1 != nullptr, "prev_flow given without prev images");
+    dPF.alloc(px * 8); dP1.alloc(px * 4);
+    copyIn2D(dPF.p, rowF, prevFlow, prevFlowStride, rowF, h, st);
+    copyIn2D(dP1.p, rowB, prevI1, prevI1Stride, rowB, h, st);
+    pv.enabled = true; pv.prevFlow[0] = dPF.as<float2>(); pv.prevI1[0] = dP1.as<uchar4>(); pv.prevPitch[0] = w;
+  }
+  FlowBatch fb(1, w, h, fp, pv.enabled);
+  fb.run(st, ip, pv, dF.as<float2>());
+  S360_CUDA_CHECK(cudaMemcpy2DAsync(flowOut, flowOutStride ? flowOutStride : rowF, dF.p, rowF, rowF, h, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  fb.checkSweepError();
+  S360_API_END
+}
+// Device pointers: images BGRA8 with a row stride in bytes (multiple of 4), flow output dense w*h float2. Enqueued on the context
+// stream; the solver object for (algorithm, size) is created on first use (that first call allocates and synchronises) and kept.
+int s360_flow_compute_dev(s360_ctx* c, const char* alg, const uint8_t* i0Dev, size_t i0Stride, const uint8_t* i1Dev, size_t i1Stride, int w, int h,
+                          float* flowOutDev, s360_hint hint) {
+  S360_API_BEGIN
+  useDevice(c);
+  FlowParams fp;
+  if (!flowParamsByName(alg, &fp)) throw std::runtime_error(std::string("unrecognized flow algorithm name: ") + (alg ? alg : "(null)"));
+  require(w > 0 && h > 0 && i0Dev && i1Dev && flowOutDev, "bad flow arguments");
+  if (!i0Stride) i0Stride = (size_t)w * 4;
+  if (!i1Stride) i1Stride = (size_t)w * 4;
+  require(i0Stride % 4 == 0 && i1Stride % 4 == 0 && i0Stride >= (size_t)w * 4 && i1Stride >= (size_t)w * 4, "row strides must be multiples of 4 bytes and at least a row");
+  const std::string key = std::string(alg) + ":" + std::to_string(w) + "x" + std::to_string(h);
+  auto& slot = c->flowOps[key];
+  if (!slot) slot = std::make_unique<FlowBatch>(1, w, h, fp);
+  FlowImagePtrs ip{};
+  FlowPrevPtrs pv{};
+  ip.i0[0] = reinterpret_cast<const uchar4*>(i0Dev); ip.i1[0] = reinterpret_cast<const uchar4*>(i1Dev);
+  ip.pitch0[0] = (int)(i0Stride / 4); ip.pitch1[0] = (int)(i1Stride / 4); ip.hint[0] = (int)hint;
+  slot->run(c->stream, ip, pv, reinterpret_cast<float2*>(flowOutDev));
+  S360_API_END
+}
+int s360_novel_view_chunk_dev(s360_ctx* c, const uint8_t* ovLDev, const uint8_t* ovRDev, size_t ovStride, const float* fLRDev, const float* fRLDev, int w, int h,
+                              int bufW, int camW, int numNovel, float slabDisp, uint8_t* chunkLDev, uint8_t* chunkRDev) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(ovLDev && ovRDev && fLRDev && fRLDev && chunkLDev && chunkRDev && w > 0 && h > 0 && bufW > 0, "bad novel view arguments");
+  if (!ovStride) ovStride = (size_t)w * 4;
+  require(ovStride % 4 == 0 && ovStride >= (size_t)w * 4, "row stride must be a multiple of 4 bytes and at least a row");
+  launchNovelViewChunk(c->stream, reinterpret_cast<const uchar4*>(ovLDev), reinterpret_cast<const uchar4*>(ovRDev), (int)(ovStride / 4),
+                       reinterpret_cast<const float2*>(fLRDev), reinterpret_cast<const float2*>(fRLDev), w, h, bufW, camW, numNovel, slabDisp,
+                       reinterpret_cast<uchar4*>(chunkLDev), reinterpret_cast<uchar4*>(chunkRDev), c->rt);
+  S360_API_END
+}
+int s360_project_spherical_strided(s360_ctx* c, int cam, const uint8_t* src, size_t srcStride, int sw, int sh, int sc, float l, float r, float t, float b,
+                                   int feather, uint8_t* dst, size_t dstStride, int dw, int dh) {
+  S360_API_BEGIN
+  require(src && dst && (sc == 3 || sc == 4) && sw > 0 && sh > 0 && dw > 0 && dh > 0, "bad image arguments");
+  const size_t srcRow = (size_t)sw * sc, dstRow = (size_t)dw * 4;
+  require((!srcStride || srcStride >= srcRow) && (!dstStride || dstStride >= dstRow), "stride smaller than a row");
+  // gather the rows, run the dense operator, scatter the rows (host side: the operator's copies dominate either way)
+  std::vector<uint8_t> s((size_t)sw * sh * sc), d((size_t)dw * dh * 4);
+  for (int y = 0; y < sh; ++y) std::memcpy(s.data() + y * srcRow, src + y * (srcStride ? srcStride : srcRow), srcRow);
+  if (s360_project_spherical(c, cam, s.data(), sw, sh, sc, l, r, t, b, feather, d.data(), dw, dh)) throw std::runtime_error(s360_last_error());
+  for (int y = 0; y < dh; ++y) std::memcpy(dst + y * (dstStride ? dstStride : dstRow), d.data() + y * dstRow, dstRow);
+  S360_API_END
+}
+
 int s360_novel_view_chunk(s360_ctx* c, const uint8_t* ovL, const uint8_t* ovR, const float* fLR, const float* fRL, int w, int h, int bufW,
                           int camW, int numNovel, float slabDisp, uint8_t* chunkL, uint8_t* chunkR) {
   S360_API_BEGIN

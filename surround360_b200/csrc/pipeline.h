@@ -55,6 +55,7 @@ struct s360_ctx {
   bool useGraphs = true;
   bool temporal = false;
   s360::FlowBatch::SweepProfile sweepProfile;
+  std::map<std::string, std::unique_ptr<s360::FlowBatch>> flowOps;   // s360_flow_compute_dev: one solver per (algorithm, size)
   s360::KernelProf kernelProf;          // per-kernel CUDA-event times + algorithmic bytes while `profile` is on
   float stageMs[7] = {0, 0, 0, 0, 0, 0, 0};
   std::string idScratch;

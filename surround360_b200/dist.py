@@ -9,6 +9,25 @@ def frames_for_rank(n_frames, rank, world):
     return list(range(rank, n_frames, world))
 
 
+def chain_ranges(n_frames, world, chains_per_rank):
+    """Video mode (prev_frame_data_dir != NONE): frame i needs frame i-1, so the sequence is cut into world x chains_per_rank
+    contiguous ranges (SURVEY 8e option A; scripts/batch_process_video.py:137-158 renders one such range per invocation). Returns
+    ranges[rank][chain] = (first, last_exclusive). The first frame of every range starts without history, like the first frame of a
+    video: the output deviates from a single-chain render at those world x chains_per_rank - 1 range heads (and converges again
+    within a few frames, the regularisation being a per-frame blend towards the previous flow)."""
+    total = world * chains_per_rank
+    base, extra = divmod(n_frames, total)
+    out, start = [], 0
+    for r in range(world):
+        row = []
+        for c in range(chains_per_rank):
+            n = base + (1 if r * chains_per_rank + c < extra else 0)
+            row.append((start, start + n))
+            start += n
+        out.append(row)
+    return out
+
+
 def broadcast_bytes(buf, src=0, device=None):
     """Broadcast a uint8 numpy buffer from `src` to every rank; returns the received array."""
     import torch

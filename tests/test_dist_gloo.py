@@ -53,3 +53,15 @@ def test_sharding_is_a_partition():
         assert sorted(allf) == list(range(64))
         assert max(len(sdist.frames_for_rank(64, r, world)) for r in range(world)) - \
             min(len(sdist.frames_for_rank(64, r, world)) for r in range(world)) <= 1
+
+
+def test_video_chain_ranges_are_contiguous_and_cover():
+    from surround360_b200 import dist as sdist
+    for n, world, chains in ((64, 8, 1), (1000, 8, 12), (17, 2, 4), (5, 2, 4)):
+        r = sdist.chain_ranges(n, world, chains)
+        flat = [rng for row in r for rng in row]
+        assert len(r) == world and all(len(row) == chains for row in r)
+        assert flat[0][0] == 0 and flat[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))          # contiguous, in order, no gaps
+        sizes = [b - a for a, b in flat]
+        assert max(sizes) - min(sizes) <= 1

@@ -230,3 +230,28 @@ def test_temporal_chain_of_frames(orig, frames17):
     assert np.array_equal(eq, outs[0])               # after a reset the first frame renders like NONE again
     c.close()
 
+
+
+def test_two_interleaved_temporal_chains(orig, frames17):
+    """Video mode with chains in flight (bench.py --temporal, SURVEY 8e option A): two contexts render two different frame ranges
+    interleaved; each chain must equal the oracle's chain over its own range (the previous-frame state is per context)."""
+    from conftest import RIG17
+    kw = dict(eqr_width=1400, eqr_height=700, final_eqr_width=1024, final_eqr_height=1024, enable_top=1, enable_bottom=1, sharpening=0.25)
+    roll = lambda k: [np.ascontiguousarray(np.roll(im, k, axis=1)) for im in frames17]
+    seqs = [[frames17, roll(5), roll(9)], [roll(3), frames17, roll(7)]]
+    ctxs, states = [], []
+    for _ in seqs:
+        c = api.Context(0)
+        c.load_rig(RIG17)
+        c.set_temporal(True)
+        ctxs.append(c)
+        states.append(ob.FrameState())
+    try:
+        for i in range(3):
+            for c, st, seq in zip(ctxs, states, seqs):      # frame i of chain A, then frame i of chain B, ...
+                eq = c.renderStereoPanorama(api.default_params(**kw), seq[i])
+                ref = orig.render_frame(seq[i], ob.make_params(**kw), state=st)
+                close(eq, ref.get("equirect"), f"equirect, frame {i} of an interleaved chain")
+    finally:
+        for c in ctxs:
+            c.close()

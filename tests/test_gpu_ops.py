@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle_bind as ob
+from surround360_b200 import api
 
 pytestmark = pytest.mark.gpu
 rng = np.random.default_rng(1234)
@@ -117,3 +118,62 @@ def test_errors_are_reported_not_swallowed(ctx):
         ctx.computeOpticalFlow("no_such_flow", a, a)
     with pytest.raises(api.VrCamException):
         ctx.bicubicRemapToSpherical(99, a, 8, 8, 0, 1, 0, 1)
+
+
+def test_strided_and_device_pointer_variants(ctx, orig):
+    """s360_flow_compute_strided / _dev, s360_novel_view_chunk_dev, s360_project_spherical_strided: same bits as the dense host calls."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    from surround360_b200 import synth
+    i0, i1 = synth.pair_512()
+    wide0 = np.zeros((200, 400, 4), np.uint8); wide1 = np.zeros((200, 400, 4), np.uint8)
+    wide0[:, 100:356] = i0[:200, :256]; wide1[:, 37:293] = i1[:200, :256]
+    v0, v1 = wide0[:, 100:356], wide1[:, 37:293]            # views: row stride 1600 bytes, like cv::Mat ROIs
+    dense = ctx.computeOpticalFlow("pixflow_low", np.ascontiguousarray(v0), np.ascontiguousarray(v1), hint=api.DirectionHint.LEFT)
+    assert np.array_equal(ctx.computeOpticalFlowStrided("pixflow_low", v0, v1, hint=api.DirectionHint.LEFT), dense)
+    assert np.array_equal(dense, ob.pixflow(np.ascontiguousarray(v0), np.ascontiguousarray(v1), "pixflow_low", hint=3))
+    # device pointers with a stride
+    d0 = torch.from_numpy(wide0).cuda(); d1 = torch.from_numpy(wide1).cuda()
+    out = torch.zeros((200, 256, 2), dtype=torch.float32, device="cuda")
+    for _ in range(2):   # the second call reuses the cached solver
+        ctx.flow_compute_dev("pixflow_low", d0.data_ptr() + 100 * 4, 1600, d1.data_ptr() + 37 * 4, 1600, 256, 200, out.data_ptr(), hint=api.DirectionHint.LEFT)
+        ctx.synchronize()
+        assert np.array_equal(out.cpu().numpy(), dense)
+    # novel view chunk on device pointers
+    rng = np.random.default_rng(3)
+    ovl = rng.integers(0, 256, (120, 90, 4), dtype=np.uint8); ovr = rng.integers(0, 256, (120, 90, 4), dtype=np.uint8)
+    flr = rng.normal(size=(120, 90, 2)).astype(np.float32) * 3; frl = rng.normal(size=(120, 90, 2)).astype(np.float32) * 3
+    hl, hr = ctx.combineLazyNovelViews(ovl, ovr, flr, frl, 50, 130, 45, 12.5)
+    t = [torch.from_numpy(a).cuda() for a in (ovl, ovr, flr, frl)]
+    ol = torch.zeros((120, 50, 4), dtype=torch.uint8, device="cuda"); orr = torch.zeros_like(ol)
+    ctx.novel_view_chunk_dev(t[0].data_ptr(), t[1].data_ptr(), 0, t[2].data_ptr(), t[3].data_ptr(), 90, 120, 50, 130, 45, 12.5, ol.data_ptr(), orr.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(ol.cpu().numpy(), hl) and np.array_equal(orr.cpu().numpy(), hr)
+    # projection with strides
+    src = rng.integers(0, 256, (300, 320, 3), dtype=np.uint8)
+    widesrc = np.zeros((300, 400, 3), np.uint8); widesrc[:, 40:360] = src
+    dense_p = ctx.bicubicRemapToSpherical(1, src, 96, 80, 0.3, -0.3, 0.25, -0.25, feather=10)
+    dst = np.zeros((80, 128, 4), np.uint8)
+    sv = widesrc[:, 40:360]
+    rc = api.lib().s360_project_spherical_strided(ctx.h, 1, C.c_void_p(sv.ctypes.data), C.c_size_t(sv.strides[0]), 320, 300, 3, C.c_float(0.3), C.c_float(-0.3),
+                                                  C.c_float(0.25), C.c_float(-0.25), 10, C.c_void_p(dst.ctypes.data), C.c_size_t(dst.strides[0]), 96, 80)
+    assert rc == 0 and np.array_equal(dst[:, :96], dense_p) and not dst[:, 96:].any()
+
+
+def test_pole_to_side_operator(ctx, orig):
+    """s360_pole_to_side (poleToSideFlowThread, TRSP:388-561) on its own against the oracle: feather, extension, flow, ramped warp,
+    seam blend, alpha ramp, padding."""
+    rng = np.random.default_rng(21)
+    sw, sh, fh = 700, 350, 180
+    from surround360_b200 import synth
+    tex = synth.band_limited_noise(sh + 8, sw + 40, 77)
+    tex = (255 * (tex - tex.min()) / max(tex.max() - tex.min(), 1e-6)).astype(np.uint8)
+    side = np.zeros((sh, sw, 4), np.uint8)
+    side[..., :3] = tex[:sh, :sw, None]; side[..., 3] = 255; side[:40, :, 3] = 0      # the side panorama has no data near the pole
+    fish = np.zeros((fh, sw, 4), np.uint8)
+    fish[..., :3] = tex[2:fh + 2, 5:sw + 5, None]; fish[..., 3] = 255
+    p = api.default_params(eqr_width=sw, eqr_height=sh, enable_top=1, enable_bottom=1)
+    warped, flow = ctx.poleToSideFlow(p, side, fish)
+    ow, of = orig.pole_to_side(ob.make_params(eqr_width=sw, eqr_height=sh, enable_top=1, enable_bottom=1), side, fish)
+    assert np.array_equal(flow, of)
+    assert np.array_equal(warped, ow)
