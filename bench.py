@@ -467,7 +467,7 @@ def main():
 
     # every kernel of one frame rendered ALONE on the GPU with CUDA events around each launch (s360_profile_kernels): ms per frame,
     # algorithmic bytes per frame (compulsory reads + writes) and the fraction of the HBM roofline that gives
-    ctxs[0].profile_enable(True)
+    ctxs[0].profile_enable(2)      # level 2: events around every kernel launch
     n_prof_frames = 2
     for i in range(n_prof_frames):
         ctxs[0].render_frame_dev(params, [t.data_ptr() for t in dev_in[i % n_sets]], img_w, img_h, dev_out[0].data_ptr(), dev_cube[0].data_ptr() if cw else None)
@@ -556,7 +556,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         # bounded sample on the host cores, in worker processes of their own (the GPU arm's process never loads the CPU code):
         # one round of concurrent frames of the same preset
-        P = max(1, min((os.cpu_count() or 1) // 10, 12))
+        P = max(1, min((os.cpu_count() or 1) // 16, 8))
         r = run_cpu_arm(args.preset, args.cubemap, P, 0, rig_path, frame_sets[0], max_procs=P)
         cpu_baseline = {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"],
                         "sample": cpu_arm_sample_text(r, args.preset, P), "concurrent_frames": r["procs"], "max_rss_gb_per_frame": r["maxrss_gb"]}

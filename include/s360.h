@@ -88,7 +88,8 @@ int s360_ctx_set_keep_intermediates(s360_ctx* ctx, int on);
  * are recorded on the context stream around every sweep launch of s360_render_frame*.
  * s360_profile_sweep synchronises the stream and returns the accumulated device time (ms),
  * number of launches, level-pixels processed (flows x width x height per launch) and
- * wavefront steps since s360_profile_enable(ctx, 1). */
+ * wavefront steps since s360_profile_enable(ctx, 1). on = 2 additionally brackets EVERY kernel launch of the frame with events
+ * (s360_profile_kernels); that serialises the frame's launches much more than level 1 does. */
 int s360_profile_enable(s360_ctx* ctx, int on);
 /* Whole-frame CUDA-graph replay (default on). Profiling, keep_intermediates and the stage timers
  * need the plain launch path and switch it off implicitly for the frames they cover. */
@@ -121,7 +122,7 @@ int s360_profile_sweep(s360_ctx* ctx, double* ms, unsigned long long* launches, 
 /* sweep launches (since s360_profile_enable) that the generic kernel had to repeat because an operand left the range of the
  * fast kernel's written-out div/sqrt sequences; valid after s360_profile_sweep */
 int s360_profile_sweep_fallbacks(s360_ctx* ctx, unsigned long long* fallbacks);
-/* Per-kernel table of everything launched by s360_render_frame[_dev] since s360_profile_enable(ctx, 1): a JSON array of
+/* Per-kernel table of everything launched by s360_render_frame[_dev] since s360_profile_enable(ctx, 2): a JSON array of
  * {"kernel", "ms" (CUDA events on the launching stream, summed), "algorithmic_bytes" (compulsory reads + writes of those launches),
  * "launches"}. Synchronises the stream. *needed receives the size of the text incl. the terminator; json may be NULL to query it. */
 int s360_profile_kernels(s360_ctx* ctx, char* json, size_t cap, size_t* needed);

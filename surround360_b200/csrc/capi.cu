@@ -135,6 +135,7 @@ int s360_profile_enable(s360_ctx* c, int on) {
   S360_API_BEGIN
   require(c != nullptr, "null context");
   c->profile = on != 0;
+  c->profileKernels = on >= 2;
   c->sweepProfile = FlowBatch::SweepProfile();
   c->kernelProf.clear();
   S360_API_END

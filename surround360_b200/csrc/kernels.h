@@ -213,6 +213,13 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   float2 *full_ = nullptr, *flowA_ = nullptr, *flowB_ = nullptr, *tmp_ = nullptr, *boundary_ = nullptr;
   int* progress_ = nullptr;
   int* sweepErr_ = nullptr;
+  // TMA descriptors (CUtensorMap, 128 bytes each, kept opaque here) of the two flow ping-pong planes per level, for the A/B
+  // variant of the blur's row pass (env S360_TMA=1); tmOk_[l] = the level's row pitch satisfies TMA's 16-byte stride rule
+  struct alignas(64) TensorMapBytes { unsigned char b[128]; };
+  std::vector<TensorMapBytes> tmA_, tmB_;
+  std::vector<char> tmOk_;
+  bool useTma_ = false;
+  void buildTensorMaps();
   // frame-invariant resize coordinates / weights per pyramid level, tabulated on the host once (flow_kernels.cu: ResizeTabs)
   void* tabAlloc_ = nullptr;
   std::vector<const int*> cubSx_, cubSy_;      // [l]: cubic upsample level l+1 -> l

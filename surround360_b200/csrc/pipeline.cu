@@ -524,8 +524,8 @@ static void runFrameFromStaging(s360_ctx* c, bool wantCube) {
   uint8_t* cube = wantCube ? F.outCube.as<uint8_t>() : nullptr;
   const bool useGraph = c->useGraphs && !c->profile && !c->keepIntermediates;
   if (!useGraph) {
-    c->kernelProf.on = c->profile;
-    t_kernelProf = c->profile ? &c->kernelProf : nullptr;   // launches of this frame are made by this thread
+    c->kernelProf.on = c->profileKernels;
+    t_kernelProf = c->profileKernels ? &c->kernelProf : nullptr;   // launches of this frame are made by this thread
     try {
       enqueueFrame(c, dev.data(), F.outEq.as<uint8_t>(), cube, true);
     } catch (...) {

@@ -52,6 +52,7 @@ struct s360_ctx {
   int poleMaskW = 0, poleMaskH = 0;
   bool keepIntermediates = false;
   bool profile = false;
+  bool profileKernels = false;          // s360_profile_enable(ctx, 2): events around every kernel launch (s360_profile_kernels)
   bool useGraphs = true;
   bool temporal = false;
   s360::FlowBatch::SweepProfile sweepProfile;

@@ -103,6 +103,8 @@ def rewrite_launches(src, modes):
 
 def main(inp, outp):
     src = open(inp).read()
+    # device-only code the emulation cannot express (TMA, mbarrier) is fenced by `#ifndef S360_EMU ... #endif  // S360_EMU`
+    src = re.sub(r'#ifndef S360_EMU\n.*?#endif(?:  // S360_EMU)?\n', '', src, flags=re.S)
     for pat, rep in ASM_RULES:
         src, n = re.subn(pat, rep, src, flags=re.S)
     if 'asm' in re.sub(r'//[^\n]*', '', src).replace('emu::', ''):
