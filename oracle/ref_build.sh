@@ -35,5 +35,21 @@ $CXX $CXXFLAGS $INC -c "$HERE/ref_capi.cpp" -o "$OUT/obj/ref_capi.o" &
 pids="$pids $!"
 for p in $pids; do wait $p; done
 $CXX -pthread -o "$OUT/TestRenderStereoPanorama" "$OUT/obj/trsp_main.o" $OBJS -lz
+# The reference's renderer with the B200 flow adapter of integration/reference_tree/optical_flow/B200Flow.h selectable through
+# --side_flow_alg / --polar_flow_alg b200_pixflow_low (the translation units that call the flow factory are compiled again with
+# the factory hook pre-included; they link the product library like a maintainer's build would).
+REPO="$(cd "$HERE/.." && pwd)"
+if [ -f "$REPO/surround360_b200/libs360b200.so" ]; then
+  HOOK="-include $HERE/ref_shim/b200_factory_hook.h -I$REPO/integration/reference_tree/optical_flow -I$REPO/include"
+  B200OBJS=""
+  for s in test/TestRenderStereoPanorama.cpp optical_flow/NovelView.cpp render/PoleRemoval.cpp; do
+    o="$OUT/obj/b200_$(echo $s | tr '/' '_' | sed 's/\.cpp$/.o/')"
+    $CXX $CXXFLAGS $INC $HOOK -c "$REF/$s" -o "$o" &
+    B200OBJS="$B200OBJS $o"
+  done
+  wait
+  REST=$(for o in $OBJS; do case "$o" in *optical_flow_NovelView.o|*render_PoleRemoval.o) ;; *) echo -n "$o ";; esac; done)
+  $CXX -pthread -o "$OUT/TestRenderStereoPanorama_b200" $B200OBJS $REST -lz -L"$REPO/surround360_b200" -ls360b200 -Wl,-rpath,'$ORIGIN/../../surround360_b200'
+fi
 $CXX -pthread -shared -o "$OUT/libref.so" "$OUT/obj/ref_capi.o" $OBJS -lz
 echo "ref_build: built $OUT/TestRenderStereoPanorama and $OUT/libref.so"
