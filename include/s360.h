@@ -19,6 +19,7 @@
  *                             (source/render/ImageWarper.h:53-57, source/util/CvUtil.cpp:117-138)
  *   s360_resize_cubic      <- cv::resize(INTER_CUBIC) at TRSP:943-956
  *   s360_render_frame      <- renderStereoPanorama() (TRSP:716-972) minus file I/O
+ *   s360_hyper_preview     <- PreviewRenderer::render (source/test/TestHyperPreview.cpp:77-185)
  *   s360_rig_*             <- Camera::loadRig / RigDescription (source/render/Camera.cpp:243-254,
  *                             source/render/RigDescription.cpp:18-78)
  *
@@ -215,6 +216,14 @@ int s360_resize_cubic(s360_ctx* ctx, const uint8_t* src, int w, int h, int chann
  * BGRA8 fw x fh; warped_out BGRA8 sw x sh; flow_out (optional) int(fw*1.2) x fh float2 */
 int s360_pole_to_side(s360_ctx* ctx, const s360_params* p, const uint8_t* side_bgra, int sw, int sh,
                       const uint8_t* fisheye_bgra, int fw, int fh, uint8_t* warped_out, float* flow_out);
+
+/* TestHyperPreview (source/test/TestHyperPreview.cpp:77-185): the fast mono preview straight from the raw Bayer frames (uint16,
+ * img_w x img_h each) of the top, bottom and secondary-bottom cameras of the loaded rig: 2x2 demosaic, alpha fades, cubic
+ * projection through the precomputed equirect->camera warp (built on the first call for a size, then resident), softmax flatten,
+ * x 255/65535. out_bgr: eqr_h x eqr_w x 3 float32, the image the reference hands to imwrite. Float path: within 1e-5 relative of
+ * the CPU result (device expf), not bit-identical. */
+int s360_hyper_preview(s360_ctx* ctx, const uint16_t* raw_top, const uint16_t* raw_bottom, const uint16_t* raw_bottom2, int img_w, int img_h,
+                       int eqr_w, int eqr_h, double gamma, double softmax_coef, float* out_bgr);
 
 /* ---- whole frame ---- */
 

@@ -52,4 +52,7 @@ if [ -f "$REPO/surround360_b200/libs360b200.so" ]; then
   $CXX -pthread -o "$OUT/TestRenderStereoPanorama_b200" $B200OBJS $REST -lz -L"$REPO/surround360_b200" -ls360b200 -Wl,-rpath,'$ORIGIN/../../surround360_b200'
 fi
 $CXX -pthread -shared -o "$OUT/libref.so" "$OUT/obj/ref_capi.o" $OBJS -lz
+# the reference's TestHyperPreview behind its own small C API (its gflags clash with the renderer's: separate library)
+$CXX $CXXFLAGS $INC -c "$HERE/ref_preview_capi.cpp" -o "$OUT/obj/ref_preview_capi.o"
+$CXX -pthread -shared -o "$OUT/libref_preview.so" "$OUT/obj/ref_preview_capi.o" $OBJS -lz
 echo "ref_build: built $OUT/TestRenderStereoPanorama and $OUT/libref.so"

@@ -49,6 +49,7 @@ T CheckNotNullRV(const char* file, int line, const char* what, T t) {
 }  // namespace google
 
 #define LOG(sev) google::LogMessage(__FILE__, __LINE__, google::GLOG_##sev).stream()
+#define LOG_IF(sev, cond) !(cond) ? (void)0 : google::LogMessageVoidify() & LOG(sev)
 #define VLOG_IS_ON(n) (google::refShimVerbosity() >= (n))
 #define VLOG(n) !VLOG_IS_ON(n) ? (void)0 : google::LogMessageVoidify() & google::LogMessage(__FILE__, __LINE__, google::GLOG_INFO).stream()
 #define CHECK(cond) (cond) ? (void)0 : google::LogMessageVoidify() & google::LogMessage(__FILE__, __LINE__, google::GLOG_FATAL).stream() << "Check failed: " #cond " "

@@ -168,6 +168,8 @@ struct Size_ {
 };
 template <typename T> static inline bool operator==(const Size_<T>& a, const Size_<T>& b) { return a.width == b.width && a.height == b.height; }
 template <typename T> static inline bool operator!=(const Size_<T>& a, const Size_<T>& b) { return !(a == b); }
+template <typename T> static inline Size_<T> operator/(const Size_<T>& a, T b) { return Size_<T>(a.width / b, a.height / b); }
+template <typename T> static inline Size_<T> operator*(const Size_<T>& a, T b) { return Size_<T>(a.width * b, a.height * b); }
 typedef Size_<int> Size2i;
 typedef Size_<float> Size2f;
 typedef Size2i Size;

@@ -169,7 +169,7 @@ void remap(const Mat& src, OutputArray dstA, const Mat& map1, const Mat& map2, i
     orc::Img8 o;
     orc::remapCubic8(toImg8(src), map, o, orcBorder(borderMode));
     store(o, dst);
-  } else if (interpolation == INTER_CUBIC && src.type() == CV_32FC2 && borderMode == BORDER_CONSTANT) {
+  } else if (interpolation == INTER_CUBIC && src.depth() == CV_32F && borderMode == BORDER_CONSTANT) {
     orc::ImgF o;
     orc::remapCubicF(toImgF(src), map, o);
     store(o, dst);
@@ -241,6 +241,15 @@ void erode(const Mat& src, OutputArray dstA, const Mat& kernel) {
 }
 
 void cvtColor(const Mat& src, OutputArray dstA, int code, int) {
+  if (src.depth() == CV_32F && code == COLOR_BGR2BGRA && src.channels() == 3) {   // alpha = ColorChannel<float>::max() = 1.0f
+    Mat out(src.rows, src.cols, CV_32FC4);
+    for (int y = 0; y < src.rows; ++y) {
+      const float* s = src.ptr<float>(y); float* d = out.ptr<float>(y);
+      for (int x = 0; x < src.cols; ++x) { d[4 * x] = s[3 * x]; d[4 * x + 1] = s[3 * x + 1]; d[4 * x + 2] = s[3 * x + 2]; d[4 * x + 3] = 1.0f; }
+    }
+    dstA.ref() = out;
+    return;
+  }
   if (src.depth() != CV_8U) refShimUnsupported("cvtColor depth");
   Mat out;
   if (code == COLOR_BGR2BGRA && src.channels() == 3) {
@@ -310,7 +319,6 @@ Mat imread(const String& filename, int flags) {
   }
 }
 bool imwrite(const String& filename, const Mat& img, const std::vector<int>&) {
-  if (img.depth() != CV_8U || (img.channels() != 3 && img.channels() != 4)) refShimUnsupported("imwrite type");
   {
     bool sink = false;
     {
@@ -319,6 +327,7 @@ bool imwrite(const String& filename, const Mat& img, const std::vector<int>&) {
     }
     if (sink) { refshim::memPut(filename, img.clone()); return true; }
   }
+  if (img.depth() != CV_8U || (img.channels() != 3 && img.channels() != 4)) refShimUnsupported("imwrite type");
   try {
     const orc::Img8 t = toImg8(img);
     pngio::write(filename, t.d.data(), t.w, t.h, t.c);

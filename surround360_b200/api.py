@@ -262,6 +262,14 @@ class Context:
                                        _p(warped), _p(flow)))
         return warped, flow
 
+    def hyperPreview(self, raw_top, raw_bottom, raw_bottom2, eqr_w, eqr_h, gamma=1.0, softmax_coef=30.0):
+        """PreviewRenderer::render (TestHyperPreview.cpp:141-159): three uint16 Bayer frames -> float32 equirect (eqr_h, eqr_w, 3)."""
+        r = [_c(a, np.uint16) for a in (raw_top, raw_bottom, raw_bottom2)]
+        h, w = r[0].shape
+        out = np.zeros((eqr_h, eqr_w, 3), np.float32)
+        _check(lib().s360_hyper_preview(self.h, _p(r[0]), _p(r[1]), _p(r[2]), w, h, eqr_w, eqr_h, C.c_double(gamma), C.c_double(softmax_coef), _p(out)))
+        return out
+
     # ---- whole frame ----
     def output_size(self, params):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -457,6 +457,35 @@ int s360_novel_view_chunk(s360_ctx* c, const uint8_t* ovL, const uint8_t* ovR, c
   S360_API_END
 }
 
+// TestHyperPreview (test/TestHyperPreview.cpp:77-185): raw Bayer frames of the top / bottom / secondary-bottom cameras -> mono equirect
+int s360_hyper_preview(s360_ctx* c, const uint16_t* rawTop, const uint16_t* rawBottom, const uint16_t* rawBottom2, int imgW, int imgH, int eqrW, int eqrH,
+                       double gamma, double softmaxCoef, float* outBgr) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(c->rigLoaded, "no rig loaded");
+  require(rawTop && rawBottom && rawBottom2 && outBgr && imgW > 1 && imgH > 1 && eqrW > 0 && eqrH > 0, "bad preview arguments");
+  cudaStream_t st = c->stream;
+  if (c->previewWarpW != eqrW || c->previewWarpH != eqrH || !c->previewWarp.p) {   // the precomputed projection: once per (rig, size)
+    std::vector<float2> warp;
+    buildPreviewWarp(c->rig, eqrW, eqrH, warp);
+    c->previewWarp.ensure(warp.size() * sizeof(float2));
+    S360_CUDA_CHECK(cudaMemcpy(c->previewWarp.p, warp.data(), warp.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    c->previewWarpW = eqrW; c->previewWarpH = eqrH;
+  }
+  const size_t rawBytes = (size_t)imgW * imgH * 2, layerPx = (size_t)(imgW / 2) * (imgH / 2);
+  DeviceBuffer dRaw(rawBytes * 3), dLayers(layerPx * 16 * 3), dOut((size_t)eqrW * eqrH * 12);
+  const uint16_t* raws[3] = {rawTop, rawBottom, rawBottom2};
+  const uint16_t* rawDev[3];
+  for (int i = 0; i < 3; ++i) {
+    S360_CUDA_CHECK(cudaMemcpyAsync(dRaw.as<uint8_t>() + i * rawBytes, raws[i], rawBytes, cudaMemcpyHostToDevice, st));
+    rawDev[i] = reinterpret_cast<const uint16_t*>(dRaw.as<uint8_t>() + i * rawBytes);
+  }
+  launchPreview(st, rawDev, imgW, imgH, (float)gamma, dLayers.as<float4>(), c->previewWarp.as<float2>(), eqrW, eqrH, (float)softmaxCoef, c->rt, dOut.as<float>());
+  S360_CUDA_CHECK(cudaMemcpyAsync(outBgr, dOut.p, (size_t)eqrW * eqrH * 12, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
 int s360_flatten_deghost(s360_ctx* c, const uint8_t* base, const uint8_t* top, int w, int h, uint8_t* out) {
   S360_API_BEGIN
   useDevice(c);

@@ -159,6 +159,12 @@ struct ProfScope {
 // usage: { S360_PROF(st, "k_name", bytes); k_name<<<...>>>(...); }
 #define S360_PROF(st, name, bytes) ::s360::ProfScope S360_PROF_CAT(_prof_, __LINE__)(st, name, (double)(bytes))
 
+struct Rig;
+// TestHyperPreview (preview_kernels.cu)
+void buildPreviewWarp(const Rig& rig, int eqrW, int eqrH, std::vector<float2>& out);
+void launchPreview(cudaStream_t st, const uint16_t* const rawDev[3], int imgW, int imgH, float gamma, float4* layers, const float2* warpDev, int eqrW,
+                   int eqrH, float softmaxCoef, const RemapTables& rt, float* outDev);
+
 class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved concurrently
  public:
   // temporal: allocate the previous-flow / motion pyramids; levelDump: allocate per-level dump planes

@@ -48,6 +48,8 @@ struct s360_ctx {
   s360::RemapTables rt{};
   std::map<int, std::unique_ptr<s360::DeviceBuffer>> blurKernels;  // erodeSize -> 8.8 fixed-point taps
   std::unique_ptr<s360::FramePlan> plan;
+  s360::DeviceBuffer previewWarp;       // s360_hyper_preview: equirect -> camera warp of the three preview cameras
+  int previewWarpW = 0, previewWarpH = 0;
   s360::DeviceBuffer poleMasks;         // two BGR8 masks (bottom, bottom2), s360_set_pole_masks
   int poleMaskW = 0, poleMaskH = 0;
   bool keepIntermediates = false;

@@ -199,3 +199,23 @@ class Frame:
 
     def __del__(self):
         self.close()
+
+
+# ---- TestHyperPreview of the reference (oracle/_ref/libref_preview.so, oracle/ref_preview_capi.cpp) ----
+REF_PREVIEW_SO = os.path.join(ORACLE_DIR, "_ref", "libref_preview.so")
+_PLIB = None
+
+
+def hyper_preview(rig_json, raw_top, raw_bottom, raw_bottom2, eqr_w, eqr_h, gamma=1.0, softmax_coef=30.0):
+    """PreviewRenderer::render of the compiled reference: three uint16 Bayer frames -> float32 (eqr_h, eqr_w, 3)."""
+    global _PLIB
+    if _PLIB is None:
+        available()
+        _PLIB = C.CDLL(REF_PREVIEW_SO)
+        _PLIB.refp_last_error.restype = C.c_char_p
+    r = [_c(a, np.uint16) for a in (raw_top, raw_bottom, raw_bottom2)]
+    h, w = r[0].shape
+    out = np.zeros((eqr_h, eqr_w, 3), np.float32)
+    if _PLIB.refp_render(rig_json.encode(), P(r[0]), P(r[1]), P(r[2]), w, h, eqr_w, eqr_h, C.c_double(gamma), C.c_double(softmax_coef), P(out)):
+        raise RuntimeError(_PLIB.refp_last_error().decode())
+    return out

@@ -1,0 +1,36 @@
+"""TestHyperPreview (test/TestHyperPreview.cpp:77-185) on the GPU against the reference's own code (oracle/_ref).
+Float path with the device's expf in the softmax blend: stated tolerance 1e-5 relative (+1e-6 absolute); the precomputed warp,
+the demosaic (including the reference's `2^16-1` = 13 XOR constant), the fades and the cubic remap are exact."""
+import numpy as np
+import pytest
+
+import ref_bind as rb
+from conftest import RIG17
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not rb.available(), reason="oracle/_ref not built")]
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _raws(seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:2048, 0:2048]
+    out = []
+    for k in range(3):   # smooth structure + noise, 12-bit Bayer values
+        base = 2000 + 1500 * np.sin(xx / (37.0 + 11 * k)) * np.cos(yy / (53.0 - 7 * k))
+        out.append(np.clip(base + rng.normal(0, 60, base.shape), 0, 4095).astype(np.uint16))
+    return out
+
+
+@pytest.mark.parametrize("size,gamma", [((512, 256), 1.0), ((1024, 512), 1.0), ((600, 300), 0.8)])
+def test_hyper_preview_matches_the_reference_build(ctx, size, gamma):
+    raws = _raws(size[0])
+    ref = rb.hyper_preview(RIG17, *raws, size[0], size[1], gamma=gamma, softmax_coef=30.0)
+    got = ctx.hyperPreview(*raws, size[0], size[1], gamma=gamma, softmax_coef=30.0)
+    assert got.shape == ref.shape
+    assert np.array_equal(np.isnan(got), np.isnan(ref))            # pixels no preview camera sees: 0 / 0 in both
+    ok = ~np.isnan(ref)
+    tol = RTOL if gamma == 1.0 else 2e-4                            # powf is a device library function too when gamma != 1
+    err = np.abs(got[ok] - ref[ok]) / (np.abs(ref[ok]) + ATOL / tol)
+    assert err.max() <= tol, f"max relative error {err.max():.3g}"
+    assert np.abs(ref[ok]).max() > 1.0                              # the frame is not trivially empty
