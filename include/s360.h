@@ -20,6 +20,8 @@
  *   s360_resize_cubic      <- cv::resize(INTER_CUBIC) at TRSP:943-956
  *   s360_render_frame      <- renderStereoPanorama() (TRSP:716-972) minus file I/O
  *   s360_hyper_preview     <- PreviewRenderer::render (source/test/TestHyperPreview.cpp:77-185)
+ *   s360_isp_*             <- CameraIsp (source/camera_isp/CameraIsp.h:44-1301) as driven by Raw2Rgb's CPU branch
+ *                             (source/camera_isp/Raw2Rgb.cpp:445-456)
  *   s360_rig_*             <- Camera::loadRig / RigDescription (source/render/Camera.cpp:243-254,
  *                             source/render/RigDescription.cpp:18-78)
  *
@@ -224,6 +226,33 @@ int s360_pole_to_side(s360_ctx* ctx, const s360_params* p, const uint8_t* side_b
  * the CPU result (device expf), not bit-identical. */
 int s360_hyper_preview(s360_ctx* ctx, const uint16_t* raw_top, const uint16_t* raw_bottom, const uint16_t* raw_bottom2, int img_w, int img_h,
                        int eqr_w, int eqr_h, double gamma, double softmax_coef, float* out_bgr);
+
+/* ---- soft ISP: raw Bayer -> RGB, the step in front of the render path ----
+ * s360_isp mirrors the reference's CameraIsp object (source/camera_isp/CameraIsp.h): constructed from the ISP configuration JSON
+ * (res/config/isp/<name>.json) and the output depth (8 or 16), configured through the same setters, then fed frames. The pipeline is
+ * CameraIsp::executePipeline (:1262-1272): black level, anti-vignetting, white balance, clamp and stretch, demosaic, colour matrix +
+ * tone curve, IIR unsharp mask; bit-identical to the reference build. demosaic_filter: 0 bilinear, 2 edge aware (the reference's
+ * default); 1 (frequency domain, cv::dct) is rejected. A configuration with stuckPixelRadius > 0 and stuckPixelThreshold <= 1 is
+ * rejected (sequential scan; with the shipped thresholds the reference's stuck-pixel loop never runs). */
+typedef struct s360_isp s360_isp;
+int s360_isp_create(const char* isp_json, int output_bpp, s360_isp** out);      /* CameraIsp(jsonInput, outputBpp), :428 */
+void s360_isp_destroy(s360_isp* isp);
+int s360_isp_set_bits_per_pixel(s360_isp* isp, int bits);                        /* setBitsPerPixel, :860 */
+int s360_isp_set_demosaic_filter(s360_isp* isp, int filter);                     /* setDemosaicFilter, :968 */
+int s360_isp_set_resize(s360_isp* isp, int resize);                              /* setResize, :978 (1, 2, 4, 8) */
+int s360_isp_set_tone_map(s360_isp* isp, int enable);                            /* enableToneMap / disableToneMap, :958-966 */
+int s360_isp_add_black_level_offset(s360_isp* isp, int offset);                  /* addBlackLevelOffset, :884 */
+/* The tables setup() derives, for an image of w x h after the resize (host only, no device needed): compositeCCM (9 floats, row
+ * major), toneCurveLut (4096 x 3), vignette gain of every column (w x 3) and row (h x 3). Any output may be NULL. */
+int s360_isp_tables(s360_isp* isp, int w, int h, float* ccm9, float* lut, float* vig_h, float* vig_v);
+/* loadImage + getImage (:831-857, :1275-1299). raw: in_w x in_h samples of depth_bits (8 or 16), stride_bytes between rows (0 =
+ * tightly packed); out: (in_h / resize) x (in_w / resize) x 3 of output_bpp bits, tightly packed, BGR when swizzle != 0 (the
+ * reference's default) else RGB. Host buffers; the copies and kernels run on the context's stream. */
+int s360_isp_process(s360_ctx* ctx, s360_isp* isp, const void* raw, int in_w, int in_h, int depth_bits, size_t stride_bytes, void* out, int swizzle);
+/* Same on DEVICE buffers, asynchronous on the context's stream: the 8-bit BGR output can be handed to s360_render_frame_dev without
+ * the 16-bit PNG round trip of the reference (Unpacker.cpp:187-190 -> RigDescription.cpp:97-101). */
+int s360_isp_process_dev(s360_ctx* ctx, s360_isp* isp, const void* raw_dev, int in_w, int in_h, int depth_bits, size_t stride_bytes, void* out_dev,
+                         int swizzle);
 
 /* ---- whole frame ---- */
 

@@ -5,6 +5,7 @@
 # cv2-pinned oracle/ocv.h). Outputs (git-ignored, shipped to the GPU box with the snapshot):
 #   oracle/_ref/TestRenderStereoPanorama   the reference's frame renderer (its own main(), flags, threading, file I/O)
 #   oracle/_ref/libref.so                  the reference's operators behind a small C API (oracle/ref_capi.cpp)
+#   oracle/_ref/libref_preview.so, libref_isp.so   TestHyperPreview and the soft ISP (camera_isp/CameraIsp.h) behind C APIs
 # Flags follow the reference's build (surround360_render/CMakeLists.txt: -O3 -std=c++11 -mavx, no -mfma, threads).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -55,4 +56,10 @@ $CXX -pthread -shared -o "$OUT/libref.so" "$OUT/obj/ref_capi.o" $OBJS -lz
 # the reference's TestHyperPreview behind its own small C API (its gflags clash with the renderer's: separate library)
 $CXX $CXXFLAGS $INC -c "$HERE/ref_preview_capi.cpp" -o "$OUT/obj/ref_preview_capi.o"
 $CXX -pthread -shared -o "$OUT/libref_preview.so" "$OUT/obj/ref_preview_capi.o" $OBJS -lz
+# the reference's soft ISP: camera_isp/CameraIsp.h + util/JsonUtil.cpp + the JSON library vendored in the reference tree
+$CXX $CXXFLAGS $INC -I$REF/camera_isp -c "$HERE/ref_isp_capi.cpp" -o "$OUT/obj/ref_isp_capi.o" &
+$CXX $CXXFLAGS $INC -c "$REF/util/JsonUtil.cpp" -o "$OUT/obj/util_JsonUtil.o" &
+$CXX $CXXFLAGS $INC -c "$REF/thirdparty/supereasyjson/json.cpp" -o "$OUT/obj/supereasyjson.o" &
+wait
+$CXX -pthread -shared -o "$OUT/libref_isp.so" "$OUT/obj/ref_isp_capi.o" "$OUT/obj/util_JsonUtil.o" "$OUT/obj/supereasyjson.o" $OBJS -lz
 echo "ref_build: built $OUT/TestRenderStereoPanorama and $OUT/libref.so"

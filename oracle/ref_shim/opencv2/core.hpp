@@ -18,6 +18,8 @@
 #pragma once
 #include <algorithm>
 #include <cassert>
+#include <ostream>
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -42,6 +44,7 @@ typedef uint64_t uint64;
 #define CV_32F 5
 #define CV_64F 6
 #define CV_CN_SHIFT 3
+#define CV_MAT_DEPTH_MASK 7
 #define CV_MAT_DEPTH(t) ((t) & 7)
 #define CV_MAT_CN(t) ((((t) >> CV_CN_SHIFT) & 511) + 1)
 #define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn) - 1) << CV_CN_SHIFT))
@@ -149,11 +152,14 @@ typedef Point_<float> Point2f;
 typedef Point_<double> Point2d;
 typedef Point2i Point;
 
+template <typename T, int cn> struct Vec;
 template <typename T>
 struct Point3_ {
   T x, y, z;
   Point3_() : x(0), y(0), z(0) {}
   Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
+  Point3_(const Vec<T, 3>& v);          // types.hpp: Point3_(const Vec<_Tp, 3>& v)
+  operator Vec<T, 3>() const;           //            operator Vec<_Tp, 3>() const
 };
 typedef Point3_<int> Point3i;
 typedef Point3_<float> Point3f;
@@ -227,6 +233,9 @@ template <typename T, int cn> static inline double norm(const Vec<T, cn>& v) {  
   for (int i = 0; i < cn; ++i) s += (double)v.val[i] * (double)v.val[i];
   return std::sqrt(s);
 }
+template <typename T> inline Point3_<T>::Point3_(const Vec<T, 3>& v) : x(v.val[0]), y(v.val[1]), z(v.val[2]) {}
+template <typename T> inline Point3_<T>::operator Vec<T, 3>() const { return Vec<T, 3>(x, y, z); }
+typedef Vec<short, 3> Vec3s;
 typedef Vec<uchar, 2> Vec2b;
 typedef Vec<uchar, 3> Vec3b;
 typedef Vec<uchar, 4> Vec4b;
@@ -268,6 +277,8 @@ class Mat {
   Mat(Size sz, int type) { create(sz.height, sz.width, type); }
   Mat(int rows_, int cols_, int type, const Scalar& s) { create(rows_, cols_, type); setTo(s); }
   Mat(Size sz, int type, const Scalar& s) { create(sz.height, sz.width, type); setTo(s); }
+  // user-allocated data (mat.inl.hpp): no ownership, continuous rows
+  Mat(int rows_, int cols_, int type, void* data_) : flags(type & 0xfff), dims(2), rows(rows_), cols(cols_), data((uchar*)data_) { step = (size_t)cols * elemSize(); }
   Mat(const Mat& m, const Rect& roi) : flags(m.flags), dims(2), rows(roi.height), cols(roi.width), step(m.step), buf_(m.buf_) {
     if (roi.x < 0 || roi.y < 0 || roi.width < 0 || roi.height < 0 || roi.x + roi.width > m.cols || roi.y + roi.height > m.rows)
       refShimUnsupported("Mat ROI outside the image");
@@ -359,6 +370,15 @@ class Mat {
     return m;
   }
   static Mat zeros(Size sz, int type) { return zeros(sz.height, sz.width, type); }
+  static Mat eye(int rows_, int cols_, int type) {   // single-channel identity (setIdentity)
+    Mat m = zeros(rows_, cols_, type);
+    for (int i = 0; i < std::min(rows_, cols_); ++i) {
+      if (m.type() == CV_32FC1) m.at<float>(i, i) = 1.0f;
+      else if (m.type() == CV_64FC1) m.at<double>(i, i) = 1.0;
+      else refShimUnsupported("Mat::eye type");
+    }
+    return m;
+  }
 
   // convertTo (convert.cpp): dst = saturate_cast<rtype>(src * alpha + beta); the 32F kernels take alpha and beta
   // as float (cvtScale_<.., float>) and skip the scaling when alpha == 1 and beta == 0 (plain cvt).
@@ -416,6 +436,37 @@ inline Mat Mat::mul(const Mat& m, double scale) const {
     for (int x = 0; x < cols; ++x) r.at<float>(y, x) = scale == 1.0 ? at<float>(y, x) * m.at<float>(y, x) : sc * at<float>(y, x) * m.at<float>(y, x);
   return r;
 }
+
+// Matrix product of small single-precision matrices (`A * B`, `A *= B` -> cv::gemm(A, B, 1, noArray(), 0), matmul.simd.hpp): for
+// 2 <= len <= 4 gemm's fixed-size branch forms every element as the float sum a0*b0 + a1*b1 + a2*b2 (left to right) and stores
+// (float)(t * alpha + c * beta) with alpha = 1.0, beta = 0.0 in double -- i.e. t itself. Pinned against cv2.gemm in tests/.
+static inline Mat operator*(const Mat& a, const Mat& b) {
+  if (a.type() != CV_32FC1 || b.type() != CV_32FC1 || a.cols != b.rows || a.cols < 2 || a.cols > 4 || b.cols != a.cols || a.rows != a.cols)
+    refShimUnsupported("Mat * Mat: only square 2x2..4x4 CV_32F products are restated");
+  Mat d(a.rows, b.cols, CV_32FC1);
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < b.cols; ++j) {
+      float t = a.at<float>(i, 0) * b.at<float>(0, j);
+      for (int k = 1; k < a.cols; ++k) t = t + a.at<float>(i, k) * b.at<float>(k, j);
+      d.at<float>(i, j) = (float)((double)t * 1.0 + 0.0 * 0.0);
+    }
+  return d;
+}
+static inline Mat& operator*=(Mat& a, const Mat& b) { Mat d = a * b; a = d; return a; }
+static inline void transpose(const Mat& src, Mat& dst) {
+  Mat out(src.cols, src.rows, src.type());
+  const size_t es = src.elemSize();
+  for (int y = 0; y < src.rows; ++y)
+    for (int x = 0; x < src.cols; ++x) std::memcpy(out.ptr(x) + (size_t)y * es, src.ptr(y) + (size_t)x * es, es);
+  dst = out;
+}
+// cv::dct / cv::idct are not restated: the frequency-domain demosaic (camera_isp/CameraIsp.h:1176-1196) is outside the built path
+static inline void dct(const Mat&, Mat&) { refShimUnsupported("cv::dct"); }
+static inline void idct(const Mat&, Mat&) { refShimUnsupported("cv::idct"); }
+// stream output of the types the reference logs (format irrelevant: verbose logging only)
+template <typename T> static inline std::ostream& operator<<(std::ostream& o, const Point3_<T>& p) { return o << "[" << p.x << ", " << p.y << ", " << p.z << "]"; }
+template <typename T> static inline std::ostream& operator<<(std::ostream& o, const std::vector<Point3_<T>>& v) { o << "["; for (const auto& p : v) o << p << ";"; return o << "]"; }
+static inline std::ostream& operator<<(std::ostream& o, const Mat& m) { return o << "Mat(" << m.rows << "x" << m.cols << ")"; }
 
 // Output arguments: OpenCV's OutputArray also binds to a `const Mat` lvalue (the reference flips `const vector<Mat>`
 // elements in place, CvUtil.cpp:120-127).

@@ -374,6 +374,73 @@ class Context:
         return out
 
 
+class CameraIsp:
+    """The reference's soft ISP object (camera_isp/CameraIsp.h:44-1301) on the GPU: same constructor arguments, same setters,
+    loadImage + getImage in one call. Driven like Raw2Rgb's CPU branch (Raw2Rgb.cpp:445-456):
+        isp = CameraIsp(json_text, output_bpp); isp.setBitsPerPixel(16); isp.setDemosaicFilter(2); isp.setResize(1)
+        isp.enableToneMap(); isp.addBlackLevelOffset(0); bgr = isp.getImage(ctx, raw)"""
+    BILINEAR_DM_FILTER, FREQUENCY_DM_FILTER, EDGE_AWARE_DM_FILTER = 0, 1, 2   # CameraIsp.h:35-40
+
+    def __init__(self, json_input, output_bpp=8):
+        self.h = C.c_void_p()
+        self.output_bpp = output_bpp
+        self._resize = 1
+        _check(lib().s360_isp_create(json_input.encode(), output_bpp, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().s360_isp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setBitsPerPixel(self, bits):
+        _check(lib().s360_isp_set_bits_per_pixel(self.h, bits))
+
+    def setDemosaicFilter(self, f):
+        _check(lib().s360_isp_set_demosaic_filter(self.h, f))
+
+    def setResize(self, r):
+        _check(lib().s360_isp_set_resize(self.h, r))
+        self._resize = r
+
+    def enableToneMap(self):
+        _check(lib().s360_isp_set_tone_map(self.h, 1))
+
+    def disableToneMap(self):
+        _check(lib().s360_isp_set_tone_map(self.h, 0))
+
+    def addBlackLevelOffset(self, offset):
+        _check(lib().s360_isp_add_black_level_offset(self.h, offset))
+
+    def tables(self, w, h):
+        """compositeCCM (3, 3), toneCurveLut (4096, 3), vignette gains per column (w, 3) and per row (h, 3); host only."""
+        ccm = np.zeros((3, 3), np.float32); lut = np.zeros((4096, 3), np.float32)
+        vh = np.zeros((w, 3), np.float32); vv = np.zeros((h, 3), np.float32)
+        _check(lib().s360_isp_tables(self.h, w, h, _p(ccm), _p(lut), _p(vh), _p(vv)))
+        return ccm, lut, vh, vv
+
+    def getImage(self, ctx, raw, swizzle=True):
+        """loadImage(raw) + getImage(): raw (H, W) uint8 / uint16 Bayer -> (H / resize, W / resize, 3) uint8 / uint16, BGR when swizzle."""
+        raw = np.asarray(raw)
+        if raw.ndim != 2 or raw.dtype not in (np.uint8, np.uint16):
+            raise VrCamException("input is larger that 16 bits per pixel")
+        if raw.strides[1] != raw.itemsize:
+            raw = np.ascontiguousarray(raw)
+        h, w = raw.shape
+        out = np.zeros((h // self._resize, w // self._resize, 3), np.uint8 if self.output_bpp == 8 else np.uint16)
+        _check(lib().s360_isp_process(ctx.h, self.h, C.c_void_p(raw.ctypes.data), w, h, 8 * raw.itemsize, C.c_size_t(raw.strides[0]), _p(out), int(swizzle)))
+        return out
+
+    def getImageDev(self, ctx, raw_dev_ptr, w, h, depth_bits, out_dev_ptr, stride_bytes=0, swizzle=True):
+        """Device-pointer variant, asynchronous on the context stream (s360_isp_process_dev)."""
+        _check(lib().s360_isp_process_dev(ctx.h, self.h, C.c_void_p(raw_dev_ptr), w, h, depth_bits, C.c_size_t(stride_bytes), C.c_void_p(out_dev_ptr), int(swizzle)))
+
+
 def saveFlowToFile(flow, path):  # CvUtil.cpp:159-182
     f = _c(flow, np.float32)
     _check(lib().s360_flow_save(path.encode(), _p(f), f.shape[1], f.shape[0]))

@@ -5,6 +5,7 @@
 #include <fstream>
 #include <sstream>
 #include "pipeline.h"
+#include "isp.h"
 
 using namespace s360;
 
@@ -482,6 +483,58 @@ int s360_hyper_preview(s360_ctx* c, const uint16_t* rawTop, const uint16_t* rawB
   }
   launchPreview(st, rawDev, imgW, imgH, (float)gamma, dLayers.as<float4>(), c->previewWarp.as<float2>(), eqrW, eqrH, (float)softmaxCoef, c->rt, dOut.as<float>());
   S360_CUDA_CHECK(cudaMemcpyAsync(outBgr, dOut.p, (size_t)eqrW * eqrH * 12, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+// ---- soft ISP (isp.h) ----
+struct s360_isp { s360::IspPipeline pipe; s360_isp(const char* j, int bpp) : pipe(j, bpp) {} };
+int s360_isp_create(const char* ispJson, int outputBpp, s360_isp** out) {
+  S360_API_BEGIN
+  require(ispJson && out, "null argument");
+  *out = new s360_isp(ispJson, outputBpp);
+  S360_API_END
+}
+void s360_isp_destroy(s360_isp* isp) { delete isp; }
+int s360_isp_set_bits_per_pixel(s360_isp* isp, int bits) { S360_API_BEGIN require(isp != nullptr, "null isp"); isp->pipe.setBitsPerPixel(bits); S360_API_END }
+int s360_isp_set_demosaic_filter(s360_isp* isp, int f) { S360_API_BEGIN require(isp != nullptr, "null isp"); isp->pipe.setDemosaicFilter(f); S360_API_END }
+int s360_isp_set_resize(s360_isp* isp, int r) { S360_API_BEGIN require(isp != nullptr, "null isp"); isp->pipe.setResize(r); S360_API_END }
+int s360_isp_set_tone_map(s360_isp* isp, int enable) {
+  S360_API_BEGIN
+  require(isp != nullptr, "null isp");
+  if (enable) isp->pipe.enableToneMap(); else isp->pipe.disableToneMap();
+  S360_API_END
+}
+int s360_isp_add_black_level_offset(s360_isp* isp, int o) { S360_API_BEGIN require(isp != nullptr, "null isp"); isp->pipe.addBlackLevelOffset(o); S360_API_END }
+int s360_isp_tables(s360_isp* isp, int w, int h, float* ccm9, float* lut, float* vigH, float* vigV) {
+  S360_API_BEGIN
+  require(isp != nullptr, "null isp");
+  isp->pipe.tables(w, h, ccm9, lut, vigH, vigV);
+  S360_API_END
+}
+int s360_isp_process_dev(s360_ctx* c, s360_isp* isp, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, int swizzle) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(isp != nullptr, "null isp");
+  require(inW > 0 && inH > 0, "bad image size");
+  isp->pipe.process(c->stream, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8), outDev, swizzle != 0);
+  S360_API_END
+}
+int s360_isp_process(s360_ctx* c, s360_isp* isp, const void* raw, int inW, int inH, int depthBits, size_t strideBytes, void* out, int swizzle) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(isp != nullptr && raw && out, "null argument");
+  require(inW > 0 && inH > 0 && (depthBits == 8 || depthBits == 16), "bad image size or depth");
+  cudaStream_t st = c->stream;
+  const size_t rowBytes = (size_t)inW * (depthBits / 8);
+  if (!strideBytes) strideBytes = rowBytes;
+  require(strideBytes >= rowBytes, "row stride smaller than a row");
+  const int r = isp->pipe.resize();
+  const size_t outBytes = (size_t)(inW / r) * (inH / r) * 3 * (isp->pipe.outputBpp() / 8);
+  DeviceBuffer dRaw(rowBytes * inH), dOut(outBytes);
+  S360_CUDA_CHECK(cudaMemcpy2DAsync(dRaw.p, rowBytes, raw, strideBytes, rowBytes, inH, cudaMemcpyHostToDevice, st));
+  isp->pipe.process(st, dRaw.p, inW, inH, depthBits, rowBytes, dOut.p, swizzle != 0);
+  S360_CUDA_CHECK(cudaMemcpyAsync(out, dOut.p, outBytes, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
   S360_API_END
 }

@@ -1,0 +1,608 @@
+// Soft ISP kernels and host pipeline (see isp.h). Reference: camera_isp/CameraIsp.h; every kernel cites the member it restates.
+// Float arithmetic in the reference's order, compiled with -fmad=false; indices (reflect) as MathUtil.h:41-44.
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include "isp.h"
+#include "json_mini.h"
+#include "kernels.h"
+
+namespace s360 {
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// expf with the bits of the C library (glibc >= 2.27, sysdeps/ieee754/flt-32/e_expf.c: Szabolcs Nagy's exp2f-table algorithm --
+// double arithmetic, 32-entry table, one final rounding to float). The unsharp mask's noise coring evaluates expf on arbitrary
+// floats (CameraIsp.h:1244-1259 -> Filter.h:112-118); CUDA's expf may differ from the host's in the last place, which the 8/16-bit
+// truncation after it turns into rare 1-LSB differences. The same IEEE double operations give the same bits on the device.
+// Table: T[i] = bits(2^(i/32)) - (i << 47); pinned against the host's expf in tests/test_isp_tables.py.
+// ------------------------------------------------------------------------------------------------------------------------------
+static __device__ const unsigned long long kExp2fTab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull, 0x3fef54873168b9aaull,
+    0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull,
+    0x3feea11473eb0187ull, 0x3feea589994cce13ull, 0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
+    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+__device__ __forceinline__ float expfHostBits(float x) {
+  const unsigned ux = __float_as_uint(x);
+  const unsigned abstop = (ux >> 20) & 0x7ffu;
+  if (abstop >= 0x42bu) {                                            // |x| >= 88 or NaN
+    if (ux == 0xff800000u) return 0.0f;
+    if (abstop >= 0x7f8u) return x + x;
+    if (x > __uint_as_float(0x42b17217u)) return __uint_as_float(0x7f800000u);   // x > log(2^128): overflow
+    if (x < __uint_as_float(0xc2cff1b4u)) return 0.0f;                           // x < log(2^-150): underflow
+  }
+  const double invLn2N = __longlong_as_double(0x40471547652b82feLL);             // 0x1.71547652b82fep+0 * 32
+  const double shift = __longlong_as_double(0x4338000000000000LL);               // 0x1.8p+52
+  const double c0 = __longlong_as_double(0x3ebc6af84b912394LL);                  // 0x1.c6af84b912394p-5 / 32^3
+  const double c1 = __longlong_as_double(0x3f2ebfce50fac4f3LL);                  // 0x1.ebfce50fac4f3p-3 / 32^2
+  const double c2 = __longlong_as_double(0x3f962e42ff0c52d6LL);                  // 0x1.62e42ff0c52d6p-1 / 32
+  const double z = invLn2N * (double)x;
+  double kd = z + shift;
+  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+  kd = kd - shift;
+  const double r = z - kd;
+  unsigned long long t = kExp2fTab[ki & 31u];
+  t += ki << 47;
+  const double s = __longlong_as_double((long long)t);
+  const double zz = c0 * r + c1;
+  const double r2 = r * r;
+  double y = c2 * r + 1.0;
+  y = zz * r2 + y;
+  y = y * s;
+  return (float)y;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+struct IspDev {
+  int w, h, inW, inH, resize;
+  float areaRecip;
+  float black[3], blackScale[3], wb[3], cmin[3], cmax[3];
+  unsigned char chan[4];     // channel (0 red, 1 green, 2 blue) of the pixel at (i % 2) * 2 + (j % 2)
+  float ccm[9];              // compositeCCM, row major
+  float maxVal;
+};
+__device__ __forceinline__ int ispReflect(int x, int r) { return x < 0 ? -x : x >= r ? 2 * r - x - 2 : x; }   // MathUtil.h:41-44
+__device__ __forceinline__ float ispClamp(float x, float a, float b) { return x < a ? a : x > b ? b : x; }    // MathUtil.h:36-39
+__device__ __forceinline__ int ispChan(const IspDev& P, int i, int j) { return P.chan[(i & 1) * 2 + (j & 1)]; }
+
+// loadImage/resizeInput (CameraIsp.h:338-358) + blackLevelAdjust (:1106-1126) + antiVignette (:1145-1154) + whiteBalance (:1005-1021)
+// + clampAndStretch (:1128-1143): raw samples -> the float Bayer plane the demosaic reads
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_isp_prep(const T* __restrict__ in, size_t strideBytes, IspDev P, const float* __restrict__ vigH, const float* __restrict__ vigV, float* __restrict__ raw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= P.w || i >= P.h) return;
+  const int r = P.resize > 1 ? 2 : 1;
+  float sum = 0.0f;
+  for (int k = 0; k < P.resize; ++k) {
+    const int ip = i * P.resize + k * 2;
+    const int ipp = ispReflect(ip + (i % r), P.inH);
+    const T* row = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(in) + (size_t)ipp * strideBytes);
+    for (int l = 0; l < P.resize; ++l) {
+      const int jp = j * P.resize + l * 2;
+      const int jpp = ispReflect(jp + (j % r), P.inW);
+      sum += float(row[jpp]);
+    }
+  }
+  float v = sum * P.areaRecip;
+  const int ch = ispChan(P, i, j);
+  if (v < 1.0f) v = (v - P.black[ch]) * P.blackScale[ch];
+  v = v * (vigH[j * 3 + ch] * vigV[i * 3 + ch]);
+  v = v * P.wb[ch];
+  v = ispClamp(v, 0.0f, 1.0f);
+  const float lo = P.cmin[ch], hi = P.cmax[ch];
+  const float t = ispClamp(v, lo, hi);
+  raw[(size_t)i * P.w + j] = (t - lo) / (hi - lo);
+}
+
+// colorCorrect (CameraIsp.h:1214-1242): composite CCM then the tone-curve LUT; the float index truncates like the reference's
+// implicit float -> size_t conversion
+__device__ __forceinline__ float4 ispColorCorrect(const IspDev& P, const float* __restrict__ lut, float p0, float p1, float p2) {
+  const float kRange = float(kToneCurveLutSize - 1);
+  const float t0 = ispClamp(P.ccm[0] * p0 + P.ccm[1] * p1 + P.ccm[2] * p2, 0.0f, kRange);
+  const float t1 = ispClamp(P.ccm[3] * p0 + P.ccm[4] * p1 + P.ccm[5] * p2, 0.0f, kRange);
+  const float t2 = ispClamp(P.ccm[6] * p0 + P.ccm[7] * p1 + P.ccm[8] * p2, 0.0f, kRange);
+  return make_float4(__ldg(lut + (size_t)t0 * 3), __ldg(lut + (size_t)t1 * 3 + 1), __ldg(lut + (size_t)t2 * 3 + 2), 0.0f);
+}
+__device__ __forceinline__ float ispLerpHalf(float a, float b) { return a * 0.5f + b * 0.5f; }   // lerp(a, b, 0.5f), MathUtil.h:56-59
+__device__ __forceinline__ bool ispRedGreenRow(const IspDev& P, int i) {   // CameraIsp.h:94-96
+  return (ispChan(P, i, 0) == 0 && ispChan(P, i, 1) == 1) || (ispChan(P, i, 1) == 0 && ispChan(P, i, 0) == 1);
+}
+
+// demosaicBilinearFilter (CameraIsp.h:89-148) + colorCorrect. Every neighbour the reference reads from its r / g / b planes is a
+// position where that plane holds the raw sample (reflect keeps the Bayer parity), so the raw plane is read directly.
+__global__ void __launch_bounds__(256)
+k_isp_demosaic_bilinear(const float* __restrict__ raw, IspDev P, const float* __restrict__ lut, float4* __restrict__ rgb) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= P.w || i >= P.h) return;
+  const int w = P.w, h = P.h;
+  const int i_1 = ispReflect(i - 1, h), i1 = ispReflect(i + 1, h), j_1 = ispReflect(j - 1, w), j1 = ispReflect(j + 1, w);
+  auto R = [&](int y, int x) { return __ldg(raw + (size_t)y * w + x); };
+  const int ch = ispChan(P, i, j);
+  float r, g, b;
+  if (ch == 0) {
+    r = R(i, j);
+    g = ispLerpHalf(ispLerpHalf(R(i_1, j), R(i1, j)), ispLerpHalf(R(i, j_1), R(i, j1)));
+    b = ispLerpHalf(ispLerpHalf(R(i_1, j_1), R(i1, j_1)), ispLerpHalf(R(i_1, j1), R(i1, j1)));
+  } else if (ch == 1) {
+    g = R(i, j);
+    if (ispRedGreenRow(P, i)) {
+      b = (R(i_1, j) + R(i1, j)) / 2.0f;
+      r = (R(i, j_1) + R(i, j1)) / 2.0f;
+    } else {
+      r = (R(i_1, j) + R(i1, j)) / 2.0f;
+      b = (R(i, j_1) + R(i, j1)) / 2.0f;
+    }
+  } else {
+    b = R(i, j);
+    g = ispLerpHalf(ispLerpHalf(R(i_1, j), R(i1, j)), ispLerpHalf(R(i, j_1), R(i, j1)));
+    r = ispLerpHalf(ispLerpHalf(R(i_1, j_1), R(i1, j_1)), ispLerpHalf(R(i_1, j1), R(i1, j1)));
+  }
+  rgb[(size_t)i * w + j] = ispColorCorrect(P, lut, r, g, b);
+}
+
+// demosaicEdgeAware, first loop (CameraIsp.h:191-230): vertical / horizontal green estimates and their gradients; the flag is the
+// term the homogeneity test counts (dH <= dV)
+__global__ void __launch_bounds__(256)
+k_isp_green_candidates(const float* __restrict__ raw, IspDev P, float* __restrict__ gV, float* __restrict__ gH, unsigned char* __restrict__ flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= P.w || i >= P.h) return;
+  const int w = P.w, h = P.h;
+  const int i_1 = ispReflect(i - 1, h), i1 = ispReflect(i + 1, h), i_2 = ispReflect(i - 2, h), i2 = ispReflect(i + 2, h);
+  const int j_1 = ispReflect(j - 1, w), j1 = ispReflect(j + 1, w), j_2 = ispReflect(j - 2, w), j2 = ispReflect(j + 2, w);
+  auto R = [&](int y, int x) { return __ldg(raw + (size_t)y * w + x); };
+  const float c = R(i, j);
+  float v, hz, dV, dH;
+  if (ispChan(P, i, j) == 1) {
+    v = c;
+    hz = c;
+    dV = (fabsf(R(i2, j) - c) + fabsf(c - R(i_2, j))) / 2.0f;
+    dH = (fabsf(R(i, j2) - c) + fabsf(c - R(i, j_2))) / 2.0f;
+  } else {
+    const float n = R(i_1, j), s = R(i1, j), wv = R(i, j_1), e = R(i, j1);
+    v = (n + s) / 2.0f;
+    hz = (wv + e) / 2.0f;
+    dV = fabsf(n - s) / 2.0f;
+    dH = fabsf(wv - e) / 2.0f;
+    const float u2 = R(i_2, j), d2 = R(i2, j), l2 = R(i, j_2), r2 = R(i, j2);
+    v = v + (2.0f * c - u2 - d2) / 4.0f;
+    hz = hz + (2.0f * c - l2 - r2) / 4.0f;
+    dV = dV + fabsf(-2.0f * c + u2 + d2) / 2.0f;
+    dH = dH + fabsf(-2.0f * c + l2 + r2) / 2.0f;
+  }
+  const size_t o = (size_t)i * w + j;
+  gV[o] = v;
+  gH[o] = hz;
+  flag[o] = dH <= dV ? 1 : 0;
+}
+
+// second and third loop (CameraIsp.h:231-262): 9 x 9 homogeneity vote picks the green estimate; red - green / blue - green at
+// the red / blue sites. The block stages the votes of its 8 x 32 pixels plus a 4-pixel apron (reflected indices) in shared memory.
+__global__ void __launch_bounds__(256)
+k_isp_green_select(const float* __restrict__ raw, const float* __restrict__ gV, const float* __restrict__ gH, const unsigned char* __restrict__ flag,
+                   IspDev P, float* __restrict__ green, float* __restrict__ diff) {
+  __shared__ unsigned char sm[16][40];
+  const int w = P.w, h = P.h;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  for (int t = threadIdx.y * 32 + threadIdx.x; t < 16 * 40; t += 256) {
+    const int ty = t / 40, tx = t - ty * 40;
+    const int y = ispReflect(min(by + ty - 4, h + 3), h), x = ispReflect(min(bx + tx - 4, w + 3), w);   // positions past the image feed no valid output
+    sm[ty][tx] = flag[(size_t)y * w + x];
+  }
+  __syncthreads();
+  const int j = bx + threadIdx.x, i = by + threadIdx.y;
+  if (j >= w || i >= h) return;
+  int hCount = 0;
+#pragma unroll
+  for (int l = 0; l < 9; ++l)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) hCount += sm[threadIdx.y + l][threadIdx.x + k];
+  const size_t o = (size_t)i * w + j;
+  const float g = hCount < 40 ? gV[o] : gH[o];   // diameterSquared / 2 = 81 / 2
+  green[o] = g;
+  diff[o] = ispChan(P, i, j) == 1 ? 0.0f : __ldg(raw + o) - g;
+}
+
+// last loop (CameraIsp.h:263-335): constant-hue interpolation of red and blue from the colour differences, then colorCorrect.
+// The sums keep the reference's terms and order, including the repeated (i1, j2) term of the six-tap average.
+__global__ void __launch_bounds__(256)
+k_isp_demosaic_edge_aware(const float* __restrict__ green, const float* __restrict__ diff, IspDev P, const float* __restrict__ lut, float4* __restrict__ rgb) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= P.w || i >= P.h) return;
+  const int w = P.w, h = P.h;
+  const int i_1 = ispReflect(i - 1, h), i1 = ispReflect(i + 1, h), i_2 = ispReflect(i - 2, h), i2 = ispReflect(i + 2, h);
+  const int j_1 = ispReflect(j - 1, w), j1 = ispReflect(j + 1, w), j_2 = ispReflect(j - 2, w), j2 = ispReflect(j + 2, w);
+  auto D = [&](int y, int x) { return __ldg(diff + (size_t)y * w + x); };
+  const float g = __ldg(green + (size_t)i * w + j);
+  const int ch = ispChan(P, i, j);
+  float r, b;
+  if (ch == 1) {
+    const float ch1 = (D(i_1, j_2) + D(i_1, j) + D(i_1, j2) + D(i1, j_2) + D(i1, j2) + D(i1, j2)) / 6.0f + g;
+    const float ch2 = (D(i_2, j_1) + D(i, j_1) + D(i2, j_1) + D(i_2, j1) + D(i, j1) + D(i2, j1)) / 6.0f + g;
+    if (ispRedGreenRow(P, i)) { b = ch1; r = ch2; } else { r = ch1; b = ch2; }
+  } else {
+    const float cross = (D(i_1, j_1) + D(i1, j_1) + D(i_1, j1) + D(i1, j1)) / 4.0f + g;
+    const float plus = (D(i, j) + D(i_2, j) + D(i2, j) + D(i, j_2) + D(i, j2)) / 5.0f + g;
+    if (ch == 0) { b = cross; r = plus; } else { r = cross; b = plus; }
+  }
+  rgb[(size_t)i * w + j] = ispColorCorrect(P, lut, r, g, b);
+}
+
+// 32 x 32 tile transpose of 16-byte pixels (the horizontal IIR pass runs along columns of the transposed image)
+__global__ void k_isp_transpose(const float4* __restrict__ src, int w, int h, float4* __restrict__ dst) {
+  __shared__ float4 tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int x = bx + threadIdx.x, y = by + r;
+    if (x < w && y < h) tile[r][threadIdx.x] = src[(size_t)y * w + x];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int y = by + threadIdx.x, x = bx + r;
+    if (x < w && y < h) dst[(size_t)x * h + y] = tile[threadIdx.x][r];
+  }
+}
+
+// One pass of iirLowPass<ReflectBoundary, ReflectBoundary, Vec3f> (Filter.h:38-96) along the columns of a w-wide, n-tall image:
+// causal sweep into `buf`, anticausal sweep out of it, clamped to [0, maxVal]. One thread per column; the loads of the next
+// kBatch rows are issued together ahead of the dependent lerps (v = ip * (1 - alpha) + v * alpha per channel).
+constexpr int kIspIirBatch = 8;
+__global__ void __launch_bounds__(128)
+k_isp_iir_columns(const float4* __restrict__ in, int w, int n, float alpha, float maxVal, float4* __restrict__ buf, float4* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const float om = 1.0f - alpha;
+  const float4 p0 = in[x];
+  float v0 = p0.x, v1 = p0.y, v2 = p0.z;
+  for (int j0 = 1; j0 <= n; j0 += kIspIirBatch) {
+    float4 ip[kIspIirBatch];
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 + u <= n) ip[u] = in[(size_t)ispReflect(j0 + u, n) * w + x];
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 + u <= n) {
+        v0 = ip[u].x * om + v0 * alpha;
+        v1 = ip[u].y * om + v1 * alpha;
+        v2 = ip[u].z * om + v2 * alpha;
+        buf[(size_t)ispReflect(j0 + u - 1, n) * w + x] = make_float4(v0, v1, v2, 0.0f);
+      }
+  }
+  for (int j0 = n - 2; j0 >= -1; j0 -= kIspIirBatch) {
+    float4 ip[kIspIirBatch];
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 - u >= -1) ip[u] = buf[(size_t)ispReflect(j0 - u, n) * w + x];
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 - u >= -1) {
+        v0 = ip[u].x * om + v0 * alpha;
+        v1 = ip[u].y * om + v1 * alpha;
+        v2 = ip[u].z * om + v2 * alpha;
+        out[(size_t)(j0 - u + 1) * w + x] = make_float4(ispClamp(v0, 0.0f, maxVal), ispClamp(v1, 0.0f, maxVal), ispClamp(v2, 0.0f, maxVal), 0.0f);
+      }
+  }
+}
+
+// sharpenWithIirLowPass (Filter.h:98-130) when `lp` is given, then getImage's conversion (CameraIsp.h:1275-1299): the float -> 8/16
+// bit stores truncate like the reference's implicit conversions; c0/c1/c2 = 2/1/0 when swizzling to BGR
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_isp_finish(const float4* __restrict__ rgb, const float4* __restrict__ lp, size_t n, float aR, float aG, float aB, float noiseCore, float maxVal,
+             int swizzle, T* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = rgb[i];
+  if (lp) {
+    const float4 l = lp[i];
+    const float h0 = p.x - l.x, h1 = p.y - l.y, h2 = p.z - l.z;
+    const float n0 = 1.0f - expfHostBits(-(h0 * h0 * noiseCore));
+    const float n1 = 1.0f - expfHostBits(-(h1 * h1 * noiseCore));
+    const float n2 = 1.0f - expfHostBits(-(h2 * h2 * noiseCore));
+    p.x = ispClamp(l.x + h0 * n0 * aR, 0.0f, maxVal);
+    p.y = ispClamp(l.y + h1 * n1 * aG, 0.0f, maxVal);
+    p.z = ispClamp(l.z + h2 * n2 * aB, 0.0f, maxVal);
+  }
+  const int c0 = swizzle ? 2 : 0, c2 = swizzle ? 0 : 2;
+  T* o = out + i * 3;
+  o[c0] = (T)(int)p.x;
+  o[1] = (T)(int)p.y;
+  o[c2] = (T)(int)p.z;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// host: configuration, tables (CameraIsp.h:390-715)
+// ------------------------------------------------------------------------------------------------------------------------------
+namespace {
+using jsonmini::Json;
+using jsonmini::JsonReader;
+inline float hLerp(float x0, float x1, float alpha) { return x0 * (1.0f - alpha) + x1 * alpha; }   // MathUtil.h:56-59
+inline float hClamp(float x, float a, float b) { return x < a ? a : x > b ? b : x; }
+// Four point DeCasteljau (CameraIsp.h:361-371)
+inline float hBezier(float a, float b, float c, float d, float t) {
+  return hLerp(hLerp(hLerp(a, b, t), hLerp(b, c, t), t), hLerp(hLerp(b, c, t), hLerp(c, d, t), t), t);
+}
+inline float highKey(float boost, float x) {   // :373-379
+  const float a = 0.5f, b = hClamp(0.6666f, 0.0f, 1.0f), c = hClamp(0.8333f + boost, 0.0f, 1.0f), d = 1.0f;
+  return x > 0.5f ? hBezier(a, b, c, d, (x - 0.5f) * 2.0f) : 0;
+}
+inline float lowKey(float boost, float x) {   // :381-387
+  const float a = 0.0f, b = hClamp(0.1666f + boost, 0.0f, 1.0f), c = hClamp(0.3333f, 0.0f, 1.0f), d = 0.5f;
+  return x <= 0.5f ? hBezier(a, b, c, d, x * 2.0f) : 0;
+}
+IspP3 readP3(const Json& j) {   // JsonUtil.cpp getVector: three doubles narrowed to float
+  if (j.kind != Json::Array || j.items.size() != 3) throw std::runtime_error("JSON error. Expecting a vector to be a list with 3 elements.");
+  IspP3 p;
+  p.x = (float)j.items[0]->number; p.y = (float)j.items[1]->number; p.z = (float)j.items[2]->number;
+  return p;
+}
+std::vector<IspP3> readP3List(const Json& j) {   // getCoordList
+  if (j.kind != Json::Array) throw std::runtime_error("JSON error. Expecting a list of 3-element lists.");
+  std::vector<IspP3> v;
+  for (auto& it : j.items) v.push_back(readP3(*it));
+  return v;
+}
+// cv::gemm's fixed-size branch for 3 x 3 CV_32F (matmul.simd.hpp): each element is the float sum a0*b0 + a1*b1 + a2*b2
+void mat3Mul(const float* a, const float* b, float* d) {
+  float t[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+  std::memcpy(d, t, sizeof t);
+}
+}  // namespace
+
+// BezierCurve::operator()(t) (MathUtil.h:208-215): recursive de Casteljau over all control points, per channel
+static float bezierRec(const std::vector<IspP3>& p, int c, int i, int j, float t) {
+  if (i == j) return c == 0 ? p[i].x : c == 1 ? p[i].y : p[i].z;
+  return hLerp(bezierRec(p, c, i, j - 1, t), bezierRec(p, c, i + 1, j, t), t);
+}
+void ispBezier(const std::vector<IspP3>& pts, float t, float out[3]) {
+  for (int c = 0; c < 3; ++c) out[c] = bezierRec(pts, c, 0, (int)pts.size() - 1, t);
+}
+
+IspPipeline::IspPipeline(const std::string& jsonInput, int outputBpp) : outputBpp_(outputBpp) {
+  if (outputBpp != 8 && outputBpp != 16) throw std::runtime_error("output bits per pixel must be 8 or 16");
+  auto root = JsonReader(jsonInput).read();
+  // defaults (CameraIsp.h:441-463)
+  bitsPerPixel_ = 8;
+  maxPixelValue_ = (1 << bitsPerPixel_) - 1;
+  clampMax_ = {1.0f, 1.0f, 1.0f};
+  vignetteRollOffH_.push_back({1.0f, 1.0f, 1.0f});
+  vignetteRollOffV_.push_back({1.0f, 1.0f, 1.0f});
+  whiteBalanceGain_ = {1.0f, 1.0f, 1.0f};
+  const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  std::memcpy(ccm_, eye, sizeof eye);
+  sharpeningSupport_ = 10.0f / 2048.0f;
+  gamma_ = {1.0f, 1.0f, 1.0f};
+  bayerPattern_ = "GBRG";
+  const Json* cfg = root->kind == Json::Object ? root->find("CameraIsp") : nullptr;
+  if (cfg) {
+    if (cfg->kind != Json::Object) throw std::runtime_error("JSON error. \"CameraIsp\" must be an object");
+    if (auto* v = cfg->find("bitsPerPixel")) bitsPerPixel_ = (int)v->number;
+    maxPixelValue_ = (1 << bitsPerPixel_) - 1;
+    if (auto* v = cfg->find("blackLevel")) blackLevel_ = readP3(*v);
+    if (auto* v = cfg->find("clampMin")) clampMin_ = readP3(*v);
+    if (auto* v = cfg->find("clampMax")) clampMax_ = readP3(*v);
+    if (auto* v = cfg->find("stuckPixelThreshold")) stuckPixelThreshold_ = (int)v->number;
+    if (auto* v = cfg->find("stuckPixelDarknessThreshold")) stuckPixelDarknessThreshold_ = (float)v->number;
+    if (auto* v = cfg->find("stuckPixelRadius")) stuckPixelRadius_ = 2 * (int)v->number;
+    if (auto* v = cfg->find("vignetteRollOffH")) vignetteRollOffH_ = readP3List(*v);
+    if (auto* v = cfg->find("vignetteRollOffV")) vignetteRollOffV_ = readP3List(*v);
+    if (auto* v = cfg->find("whiteBalanceGain")) whiteBalanceGain_ = readP3(*v);
+    if (auto* v = cfg->find("ccm")) {   // getMatrix
+      if (v->kind != Json::Array || v->items.size() != 3) throw std::runtime_error("JSON error. Expecting a matrix being a 3 x 3 element list: [[row1], [row2], [row3]].");
+      for (int r = 0; r < 3; ++r) {
+        const Json& row = *v->items[r];
+        if (row.kind != Json::Array || row.items.size() != 3) throw std::runtime_error("JSON error. Expecting every matrix row to be a list with 3 elements.");
+        for (int c = 0; c < 3; ++c) ccm_[r * 3 + c] = (float)row.items[c]->number;
+      }
+    }
+    if (auto* v = cfg->find("saturation")) saturation_ = (float)v->number;
+    if (auto* v = cfg->find("gamma")) gamma_ = readP3(*v);
+    if (auto* v = cfg->find("lowKeyBoost")) lowKeyBoost_ = readP3(*v);
+    if (auto* v = cfg->find("highKeyBoost")) highKeyBoost_ = readP3(*v);
+    if (auto* v = cfg->find("contrast")) contrast_ = (float)v->number;
+    if (auto* v = cfg->find("sharpening")) sharpening_ = readP3(*v);
+    if (auto* v = cfg->find("sharpeningSupport")) sharpeningSupport_ = (float)v->number;
+    if (auto* v = cfg->find("noiseCore")) noiseCore_ = (float)v->number;
+    if (auto* v = cfg->find("bayerPattern")) { if (v->kind != Json::String) throw std::runtime_error("JSON error. bayerPattern must be a string"); bayerPattern_ = v->text; }
+  }
+  setup();
+}
+
+void IspPipeline::setup() {
+  // Bayer pattern tables (CameraIsp.h:613-663); an unknown pattern leaves the reference's tables uninitialised -- refuse it here
+  struct Pat { const char* name; bool red[4], green[4]; };
+  static const Pat pats[4] = {{"RGGB", {1, 0, 0, 0}, {0, 1, 1, 0}}, {"GRBG", {0, 1, 0, 0}, {1, 0, 0, 1}}, {"GBRG", {0, 0, 1, 0}, {1, 0, 0, 1}}, {"BGGR", {0, 0, 0, 1}, {0, 1, 1, 0}}};
+  const Pat* pat = nullptr;
+  for (auto& p : pats)
+    if (bayerPattern_.find(p.name) != std::string::npos) { pat = &p; break; }
+  if (!pat) throw std::runtime_error("unknown bayerPattern: " + bayerPattern_);
+  for (int k = 0; k < 4; ++k) { redBayerPixel_[k / 2][k % 2] = pat->red[k]; greenBayerPixel_[k / 2][k % 2] = pat->green[k]; }
+  // saturation in YUV (CameraIsp.h:675-684; matrices of ColorspaceConversion.h:22-36): satMat = yuv2rgb * diag(1, s, s) * rgb2yuv
+  const float rgb2yuv[9] = {0.299f, 0.587f, 0.114f, -0.14713f, -0.28886f, 0.436f, 0.615f, -0.51499f, -0.10001f};
+  const float yuv2rgb[9] = {1.0f, 0.0f, 1.13983f, 1.0f, -0.39465f, -0.58060f, 1.0f, 2.03211f, 0.0f};
+  float satMat[9] = {1.0f, 0, 0, 0, saturation_, 0, 0, 0, saturation_}, tmp[9];
+  mat3Mul(yuv2rgb, satMat, tmp);
+  mat3Mul(tmp, rgb2yuv, satMat);
+  // transpose(ccm, compositeCCM); compositeCCM *= satMat; compositeCCM *= float(kToneCurveLutSize - 1) (:686-692)
+  float t[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) t[r * 3 + c] = ccm_[c * 3 + r];
+  mat3Mul(t, satMat, compositeCCM_);
+  const float scale = float(kToneCurveLutSize - 1);
+  for (float& v : compositeCCM_) v = v * scale;
+  buildToneCurveLut();
+}
+
+void IspPipeline::buildToneCurveLut() {
+  toneCurveLut_.assign((size_t)kToneCurveLutSize * 3, 0.0f);
+  const float range = float((1 << outputBpp_) - 1);
+  const float dx = 1.0f / float(kToneCurveLutSize - 1);
+  const float angle = M_PI * 0.25f * contrast_;
+  const float slope = tanf(angle);
+  const float bias = 0.5f * (1.0f - slope);
+  for (int i = 0; i < kToneCurveLutSize; ++i) {
+    const float x = dx * i;
+    float* o = &toneCurveLut_[(size_t)i * 3];
+    if (disableToneCurve_) {
+      const float y = x * range;
+      o[0] = o[1] = o[2] = y;
+    } else {
+      float r = powf(x, gamma_.x), g = powf(x, gamma_.y), b = powf(x, gamma_.z);
+      r = lowKey(lowKeyBoost_.x, r) + highKey(highKeyBoost_.x, r);
+      g = lowKey(lowKeyBoost_.y, g) + highKey(highKeyBoost_.y, g);
+      b = lowKey(lowKeyBoost_.z, b) + highKey(highKeyBoost_.z, b);
+      o[0] = hClamp((slope * r + bias) * range, 0.0f, range);
+      o[1] = hClamp((slope * g + bias) * range, 0.0f, range);
+      o[2] = hClamp((slope * b + bias) * range, 0.0f, range);
+    }
+  }
+  lutDirty_ = true;
+}
+
+void IspPipeline::setDemosaicFilter(int f) {
+  if (f < 0 || f >= 3) throw std::runtime_error("expecting Demosaic filter in [0,2]");
+  demosaicFilter_ = f;
+}
+void IspPipeline::setResize(int r) {
+  if (r != 1 && r != 2 && r != 4 && r != 8) throw std::runtime_error("expecting a resize value of 1, 2, 4, or 8. got " + std::to_string(r));
+  resize_ = r;
+}
+
+static void vignetteTables(const std::vector<IspP3>& ptsH, const std::vector<IspP3>& ptsV, int w, int h, std::vector<float>& out) {
+  const int maxDimension = std::max(w, h);   // CameraIsp.h:834
+  out.resize((size_t)(w + h) * 3);
+  for (int x = 0; x < w; ++x) ispBezier(ptsH, float(x) / float(maxDimension), &out[(size_t)x * 3]);
+  for (int y = 0; y < h; ++y) ispBezier(ptsV, float(y) / float(maxDimension), &out[(size_t)(w + y) * 3]);
+}
+
+void IspPipeline::tables(int w, int h, float* ccm9, float* lut, float* vigH, float* vigV) {
+  if (w < 1 || h < 1) throw std::runtime_error("bad table size");
+  std::vector<float> vig;
+  vignetteTables(vignetteRollOffH_, vignetteRollOffV_, w, h, vig);
+  if (ccm9) std::memcpy(ccm9, compositeCCM_, sizeof compositeCCM_);
+  if (lut) std::memcpy(lut, toneCurveLut_.data(), toneCurveLut_.size() * sizeof(float));
+  if (vigH) std::memcpy(vigH, vig.data(), (size_t)w * 3 * sizeof(float));
+  if (vigV) std::memcpy(vigV, vig.data() + (size_t)w * 3, (size_t)h * 3 * sizeof(float));
+}
+
+IspPipeline::~IspPipeline() {
+  if (dLut_) cudaFree(dLut_);
+  if (dVig_) cudaFree(dVig_);
+  if (dWork_) cudaFree(dWork_);
+}
+
+// per pixel: rgb, tA, tB float4 (48 B) + scratch float4 (16 B); the demosaic's temporaries (raw, gV, gH, green, diff: 5 floats, and
+// one flag byte) live in tA / tB / scratch, which the sharpen stage only needs afterwards
+void IspPipeline::ensureDevice(int w, int h) {
+  const size_t px = (size_t)w * h, need = px * 64;
+  if (need > workBytes_) {
+    if (dWork_) S360_CUDA_CHECK(cudaFree(dWork_));
+    dWork_ = nullptr; workBytes_ = 0;
+    S360_CUDA_CHECK(cudaMalloc(&dWork_, need));
+    workBytes_ = need;
+  }
+  if (!dLut_) S360_CUDA_CHECK(cudaMalloc(&dLut_, (size_t)kToneCurveLutSize * 3 * sizeof(float)));
+  if (w != vigW_ || h != vigH_ || !dVig_) {
+    if (dVig_) S360_CUDA_CHECK(cudaFree(dVig_));
+    dVig_ = nullptr;
+    S360_CUDA_CHECK(cudaMalloc(&dVig_, (size_t)(w + h) * 3 * sizeof(float)));
+    vigW_ = 0; vigH_ = 0;
+  }
+}
+
+void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle) {
+  if (depthBits != 8 && depthBits != 16) throw std::runtime_error("input is larger that 16 bits per pixel");   // the reference's message, CameraIsp.h:855
+  if (!rawDev || !outDev) throw std::runtime_error("null image");
+  if (demosaicFilter_ == 1) throw std::runtime_error("the frequency-domain demosaic filter (cv::dct) is not implemented: use 0 (bilinear) or 2 (edge aware)");
+  if (stuckPixelRadius_ > 0 && stuckPixelThreshold_ <= 1)
+    throw std::runtime_error("stuck-pixel removal with stuckPixelThreshold <= 1 is a sequential in-place scan and is not implemented");
+  // (with stuckPixelThreshold >= 2 the reference's candidate loop `for (k = size - 1; k <= size - threshold; k--)` never runs:
+  //  removeStuckPixels changes nothing, CameraIsp.h:1090-1097)
+  const int w = inW / resize_, h = inH / resize_;   // loadImage, CameraIsp.h:832-833
+  if (w < 8 || h < 8) throw std::runtime_error("image too small for the ISP (8 x 8 after the resize at least)");
+  if (strideBytes < (size_t)inW * (depthBits / 8)) throw std::runtime_error("row stride smaller than a row");
+  // loadImage: the input depth overrides bitsPerPixel; only the 16-bit case recomputes maxPixelValue (CameraIsp.h:843-853)
+  if (depthBits == 8) bitsPerPixel_ = 8;
+  else { bitsPerPixel_ = 16; maxPixelValue_ = (1 << bitsPerPixel_) - 1; }
+  ensureDevice(w, h);
+  if (lutDirty_) {
+    S360_CUDA_CHECK(cudaMemcpyAsync(dLut_, toneCurveLut_.data(), toneCurveLut_.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    S360_CUDA_CHECK(cudaStreamSynchronize(st));   // the host vector may be rebuilt right after the call
+    lutDirty_ = false;
+  }
+  if (vigW_ != w || vigH_ != h) {
+    std::vector<float> vig;
+    vignetteTables(vignetteRollOffH_, vignetteRollOffV_, w, h, vig);
+    S360_CUDA_CHECK(cudaMemcpyAsync(dVig_, vig.data(), vig.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    S360_CUDA_CHECK(cudaStreamSynchronize(st));
+    vigW_ = w; vigH_ = h;
+  }
+  IspDev P;
+  P.w = w; P.h = h; P.inW = inW; P.inH = inH; P.resize = resize_;
+  P.areaRecip = 1.0f / (maxPixelValue_ * float(resize_ * resize_));   // CameraIsp.h:340
+  const float bl[3] = {blackLevel_.x, blackLevel_.y, blackLevel_.z};
+  for (int c = 0; c < 3; ++c) {   // blackLevelAdjust's constants, :1107-1112
+    P.black[c] = bl[c] / float(maxPixelValue_);
+    P.blackScale[c] = 1.0f / (1.0f - P.black[c]);
+  }
+  P.wb[0] = whiteBalanceGain_.x; P.wb[1] = whiteBalanceGain_.y; P.wb[2] = whiteBalanceGain_.z;
+  P.cmin[0] = clampMin_.x; P.cmin[1] = clampMin_.y; P.cmin[2] = clampMin_.z;
+  P.cmax[0] = clampMax_.x; P.cmax[1] = clampMax_.y; P.cmax[2] = clampMax_.z;
+  for (int k = 0; k < 4; ++k) P.chan[k] = redBayerPixel_[k / 2][k % 2] ? 0 : greenBayerPixel_[k / 2][k % 2] ? 1 : 2;
+  std::memcpy(P.ccm, compositeCCM_, sizeof P.ccm);
+  P.maxVal = (1 << outputBpp_) - 1.0f;   // sharpen(), CameraIsp.h:1248
+
+  const size_t px = (size_t)w * h;
+  float4* rgb = reinterpret_cast<float4*>(dWork_);
+  float4* tA = rgb + px;
+  float4* tB = tA + px;
+  float4* scratch = tB + px;
+  float* raw = reinterpret_cast<float*>(tA);         // demosaic temporaries, dead before the sharpen stage writes tA / tB / scratch
+  float* gV = raw + px;
+  float* gH = gV + px;
+  float* green = gH + px;
+  float* diff = reinterpret_cast<float*>(tB);
+  unsigned char* flag = reinterpret_cast<unsigned char*>(scratch);
+  const float* vigH = dVig_;
+  const float* vigV = dVig_ + (size_t)w * 3;
+  const dim3 b(32, 8), g(iDivUp(w, 32), iDivUp(h, 8));
+  {
+    S360_PROF(st, "k_isp_prep", (double)px * (depthBits / 8) * resize_ * resize_ + (double)px * 4);
+    if (depthBits == 8) k_isp_prep<unsigned char><<<g, b, 0, st>>>(reinterpret_cast<const unsigned char*>(rawDev), strideBytes, P, vigH, vigV, raw);
+    else k_isp_prep<unsigned short><<<g, b, 0, st>>>(reinterpret_cast<const unsigned short*>(rawDev), strideBytes, P, vigH, vigV, raw);
+  }
+  if (demosaicFilter_ == 0) {
+    S360_PROF(st, "k_isp_demosaic_bilinear", (double)px * (4 + 16));
+    k_isp_demosaic_bilinear<<<g, b, 0, st>>>(raw, P, dLut_, rgb);
+    g_launchCount += 2;
+  } else {
+    { S360_PROF(st, "k_isp_green_candidates", (double)px * (4 + 9)); k_isp_green_candidates<<<g, b, 0, st>>>(raw, P, gV, gH, flag); }
+    { S360_PROF(st, "k_isp_green_select", (double)px * (13 + 8)); k_isp_green_select<<<g, b, 0, st>>>(raw, gV, gH, flag, P, green, diff); }
+    { S360_PROF(st, "k_isp_demosaic_edge_aware", (double)px * (8 + 16)); k_isp_demosaic_edge_aware<<<g, b, 0, st>>>(green, diff, P, dLut_, rgb); }
+    g_launchCount += 4;
+  }
+  const float4* lp = nullptr;
+  if (sharpening_.x != 0.0 && sharpening_.y != 0.0 && sharpening_.z != 0.0) {   // sharpen(), CameraIsp.h:1244-1259
+    const float alpha = powf(sharpeningSupport_, 1.0f / 4.0f);                  // Filter.h:46
+    const dim3 tb(32, 8);
+    { S360_PROF(st, "k_isp_transpose", (double)px * 32); k_isp_transpose<<<dim3(iDivUp(w, 32), iDivUp(h, 32)), tb, 0, st>>>(rgb, w, h, tA); }             // tA: h wide, w tall
+    { S360_PROF(st, "k_isp_iir_columns", (double)px * 64); k_isp_iir_columns<<<iDivUp(h, 128), 128, 0, st>>>(tA, h, w, alpha, P.maxVal, scratch, tB); }     // horizontal pass
+    { S360_PROF(st, "k_isp_transpose", (double)px * 32); k_isp_transpose<<<dim3(iDivUp(h, 32), iDivUp(w, 32)), tb, 0, st>>>(tB, h, w, tA); }             // tA: w wide, h tall
+    { S360_PROF(st, "k_isp_iir_columns", (double)px * 64); k_isp_iir_columns<<<iDivUp(w, 128), 128, 0, st>>>(tA, w, h, alpha, P.maxVal, scratch, tB); }     // vertical pass
+    lp = tB;
+    g_launchCount += 4;
+  }
+  {
+    S360_PROF(st, "k_isp_finish", (double)px * ((lp ? 32 : 16) + 3 * (outputBpp_ / 8)));
+    const unsigned blocks = (unsigned)((px + 255) / 256);
+    const float aR = 1.0f + sharpening_.x, aG = 1.0f + sharpening_.y, aB = 1.0f + sharpening_.z;
+    if (outputBpp_ == 8) k_isp_finish<unsigned char><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned char*>(outDev));
+    else k_isp_finish<unsigned short><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned short*>(outDev));
+    ++g_launchCount;
+  }
+  S360_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace s360

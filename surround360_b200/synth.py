@@ -149,3 +149,24 @@ def pair_512(seed=1):
     def pack(I):
         return np.ascontiguousarray(np.concatenate([I.clip(0, 255), a[..., None]], -1).astype(np.uint8))
     return pack(I0), pack(I1)
+
+
+def bayer_frame(h, w, dtype=np.uint16, seed=0):
+    """A synthetic raw Bayer frame (pattern-agnostic: every photosite gets the scene value of 'its' colour under GBRG, which is just
+    a textured mosaic under any other pattern): smooth colour gradients + band-limited texture + shot-like noise, with a saturated
+    patch, a near-black patch below the black level and a few hot pixels so that the ISP's clamps and its `v < 1` test are exercised."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    tex = band_limited_noise(h, w, seed + 11)
+    tex = (tex - tex.min()) / max(float(tex.max() - tex.min()), 1e-6)
+    r = 0.15 + 0.7 * xx / max(w - 1, 1) * (0.6 + 0.4 * tex)
+    g = 0.10 + 0.8 * (0.5 + 0.5 * np.sin(xx / 17.0 + yy / 23.0)) * (0.5 + 0.5 * tex)
+    b = 0.12 + 0.7 * yy / max(h - 1, 1) * (0.7 + 0.3 * tex)
+    mosaic = np.where((yy % 2 == 1) & (xx % 2 == 0), r, np.where((yy % 2 == 0) & (xx % 2 == 1), b, g))
+    mosaic = mosaic + rng.normal(0, 0.01, (h, w)).astype(np.float32) * np.sqrt(np.maximum(mosaic, 0.01))
+    mosaic[h // 5:h // 5 + max(h // 8, 4), w // 6:w // 6 + max(w // 7, 4)] = 1.2      # saturated
+    mosaic[h // 2:h // 2 + max(h // 9, 4), w // 2:w // 2 + max(w // 6, 4)] *= 0.01    # below the black level
+    flat = mosaic.reshape(-1)
+    flat[rng.integers(0, flat.size, max(flat.size // 4000, 3))] = 1.0                 # hot pixels
+    full = 65535.0 if dtype == np.uint16 else 255.0
+    return np.clip(0.02 * full + mosaic * 0.9 * full, 0, full).astype(dtype)

@@ -219,3 +219,42 @@ def hyper_preview(rig_json, raw_top, raw_bottom, raw_bottom2, eqr_w, eqr_h, gamm
     if _PLIB.refp_render(rig_json.encode(), P(r[0]), P(r[1]), P(r[2]), w, h, eqr_w, eqr_h, C.c_double(gamma), C.c_double(softmax_coef), P(out)):
         raise RuntimeError(_PLIB.refp_last_error().decode())
     return out
+
+
+# ---- the reference's soft ISP (camera_isp/CameraIsp.h; oracle/_ref/libref_isp.so, oracle/ref_isp_capi.cpp) ----
+REF_ISP_SO = os.path.join(ORACLE_DIR, "_ref", "libref_isp.so")
+_ILIB = None
+
+
+def _isp_lib():
+    global _ILIB
+    if _ILIB is None:
+        available()
+        if not os.path.exists(REF_ISP_SO):
+            raise RuntimeError("oracle/_ref/libref_isp.so is missing (oracle/ref_build.sh)")
+        _ILIB = C.CDLL(REF_ISP_SO)
+        _ILIB.refisp_last_error.restype = C.c_char_p
+    return _ILIB
+
+
+def isp_process(json_text, raw, demosaic_filter=2, resize=1, output_bpp=8, tone_curve=True, black_level_offset=0, swizzle=True):
+    """Raw2Rgb's CPU branch (Raw2Rgb.cpp:445-456): raw Bayer uint8/uint16 (h, w) -> (h/resize, w/resize, 3) uint8/uint16."""
+    L = _isp_lib()
+    raw = np.ascontiguousarray(raw)
+    assert raw.dtype in (np.uint8, np.uint16) and raw.ndim == 2
+    h, w = raw.shape
+    out = np.zeros((h // resize, w // resize, 3), np.uint8 if output_bpp == 8 else np.uint16)
+    if L.refisp_process(json_text.encode(), P(raw), w, h, 8 if raw.dtype == np.uint8 else 16, demosaic_filter, resize, output_bpp, int(tone_curve),
+                        black_level_offset, int(swizzle), P(out)):
+        raise RuntimeError(L.refisp_last_error().decode())
+    return out
+
+
+def isp_tables(json_text, w, h, output_bpp=8, tone_curve=True):
+    """Tables CameraIsp::setup() derives: compositeCCM (3, 3), toneCurveLut (4096, 3), vignette gains per column (w, 3) and row (h, 3)."""
+    L = _isp_lib()
+    ccm = np.zeros((3, 3), np.float32); lut = np.zeros((4096, 3), np.float32)
+    vh = np.zeros((w, 3), np.float32); vv = np.zeros((h, 3), np.float32)
+    if L.refisp_tables(json_text.encode(), output_bpp, int(tone_curve), w, h, P(ccm), P(lut), P(vh), P(vv)):
+        raise RuntimeError(L.refisp_last_error().decode())
+    return ccm, lut, vh, vv

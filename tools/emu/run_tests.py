@@ -20,7 +20,7 @@ def build():
     objs = []
     common = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-c", "-I", os.path.join(HERE, "stub"), "-I", CSRC,
               "-I", os.path.join(ROOT, "include")]
-    for name in ("warp_kernels", "finish_kernels", "flow_kernels", "preview_kernels", "pipeline", "capi"):
+    for name in ("warp_kernels", "finish_kernels", "flow_kernels", "preview_kernels", "isp_kernels", "pipeline", "capi"):
         gen = os.path.join(BUILD, name + "_emu.cpp")
         subprocess.check_call([sys.executable, os.path.join(HERE, "emu_prep.py"), os.path.join(CSRC, name + ".cu"), gen], stdout=subprocess.DEVNULL)
         obj = os.path.join(BUILD, name + "_emu.o")
