@@ -18,6 +18,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -295,6 +296,85 @@ def side_pass(api, torch, dev, local_rank, blob_host, frame_sets, preset, cubema
     return r
 
 
+ISP_CONFIG = {"CameraIsp": {   # a 16-bit GBRG sensor in the schema of the reference's res/config/isp/*.json (values written here)
+    "bitsPerPixel": 16, "blackLevel": [1310.0, 1290.0, 1275.0],
+    "vignetteRollOffH": [[1.12, 1.10, 1.08], [1.02, 1.01, 1.0], [1.0, 1.0, 1.0], [1.01, 1.02, 1.0], [1.09, 1.11, 1.13]],
+    "vignetteRollOffV": [[1.15, 1.12, 1.1], [1.0, 1.0, 1.0], [1.0, 1.0, 1.0], [1.07, 1.09, 1.11]],
+    "whiteBalanceGain": [1.17, 1.0, 1.58], "stuckPixelThreshold": 5, "stuckPixelDarknessThreshold": 0.11, "stuckPixelRadius": 0,
+    "ccm": [[1.04, -0.06, 0.02], [0.15, 1.12, -0.27], [-0.14, -0.09, 1.23]], "sharpening": [0.5, 0.45, 0.55], "saturation": 1.2, "contrast": 1.0,
+    "lowKeyBoost": [-0.2, -0.15, -0.2], "highKeyBoost": [0.2, 0.2, 0.15], "gamma": [0.4545, 0.46, 0.45], "bayerPattern": "GBRG"}}
+
+ISP_CPU_SNIPPET = """
+import sys, time, json, zlib
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ref_bind as rb
+from surround360_b200 import synth
+raw = synth.bayer_frame(2048, 2048, np.uint16, seed=5)
+cfg = %r
+rb.isp_process(cfg, raw[:256, :256], 2, 1, 16)
+t0 = time.perf_counter(); n = 0
+while n < 3:
+    out = rb.isp_process(cfg, raw, 2, 1, 16); n += 1
+print(json.dumps({"seconds_per_image": (time.perf_counter() - t0) / n, "crc32": format(zlib.crc32((out >> 8).astype(np.uint8).tobytes()), "08x")}))
+"""
+
+
+def isp_pass(api, torch, dev, local_rank, peak, cpu=True):
+    """the soft ISP in front of the renderer. One 'frame' = the rig's 17 raw 2048 x 2048 16-bit Bayer images -> BGR8 renderer
+    input (edge-aware demosaic, tone curve, IIR unsharp mask; 16-bit pipeline narrowed to the high byte like the reference's PNG hand-off),
+    device resident, timed with CUDA events on the context's stream. CPU sample: the reference's own CameraIsp (oracle/_ref) on one image,
+    one thread (the reference runs one camera per thread, Unpacker.cpp:118), in a subprocess."""
+    from surround360_b200 import synth
+    ctx = api.Context(local_rank)
+    cfg = json.dumps(ISP_CONFIG)
+    isp = api.CameraIsp(cfg, 16)
+    isp.setBitsPerPixel(16); isp.setDemosaicFilter(2); isp.setResize(1); isp.enableToneMap()
+    n_cam, w, h = 17, 2048, 2048
+    raws = [torch.from_numpy(synth.bayer_frame(h, w, np.uint16, seed=5 + (k % 3)).view(np.int16)).to(dev) for k in range(n_cam)]
+    outs = [torch.empty((h, w, 3), dtype=torch.uint8, device=dev) for _ in range(n_cam)]
+    st = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def frame():
+        for r, o in zip(raws, outs):
+            isp.frameImageDev(ctx, r.data_ptr(), w, h, 16, o.data_ptr())
+    for _ in range(3):
+        frame()
+    ctx.synchronize()
+    K = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(K):
+        frame()
+    e1.record(st)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    crc = format(zlib.crc32(outs[0].cpu().numpy().tobytes()), "08x")
+    # per-kernel device time of one frame (events around every launch)
+    ctx.profile_enable(2)
+    frame()
+    ctx.synchronize()
+    kern = []
+    for r in ctx.profile_kernels():
+        if r["kernel"].startswith("k_isp"):
+            gbs = r["algorithmic_bytes"] / 1e9 / (r["ms"] / 1e3) if r["ms"] > 0 else 0.0
+            kern.append({"kernel": r["kernel"], "launches_per_frame": r["launches"], "ms_per_frame_alone": r["ms"], "algorithmic_gb_per_frame": r["algorithmic_bytes"] / 1e9,
+                         "achieved_gbs": gbs, "frac": gbs / peak})
+    ctx.profile_enable(0)
+    isp.close(); ctx.close()
+    res = {"workload": "17 raw 2048x2048 uint16 GBRG frames -> BGR8 (edge-aware demosaic, CCM + tone curve, IIR unsharp mask), inputs and outputs resident in HBM",
+           "ms_per_rig_frame": ms, "raw_mp_per_s": n_cam * w * h / 1e6 / (ms / 1e3), "rig_frames_per_s": 1000.0 / ms, "launches_per_rig_frame": 10 * n_cam,
+           "output_crc32_cam0": crc, "kernels": sorted(kern, key=lambda k: -k["ms_per_frame_alone"])}
+    if cpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_isp.so")):
+        r = subprocess.run([sys.executable, "-c", ISP_CPU_SNIPPET % (os.path.join(ROOT, "tests"), ROOT, cfg)], capture_output=True, text=True, timeout=600)
+        if r.returncode == 0:
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            res["cpu_baseline"] = {"value": w * h / 1e6 / j["seconds_per_image"], "unit": "raw MP/s", "cores": 1, "kind": "reference",
+                                   "sample": "3 x one 2048x2048 image through the reference's CameraIsp (oracle/_ref/libref_isp.so), one thread"}
+            res["matches_cpu_reference"] = j["crc32"] == crc   # camera 0 is the image of the CPU sample (seed 5)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,6 +388,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--temporal", action="store_true", help="video mode: every context is a chain (frame i regularises against frame i-1 of its context)")
     ap.add_argument("--no-extras", action="store_true", help="skip the short 6k / cubemap passes appended to the headline line")
+    ap.add_argument("--isp-only", action="store_true", help="only the soft-ISP pass of the extras (SURVEY 8 f2): prints its JSON object")
     ap.add_argument("--cpu-arm-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--worker-kind", default="reference", help=argparse.SUPPRESS)
     ap.add_argument("--rig", default="", help=argparse.SUPPRESS)
@@ -334,6 +415,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.isp_only:
+        print(json.dumps(isp_pass(api, torch, dev, local_rank, peaks()[0], cpu=not args.no_cpu_baseline)), flush=True)
+        return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -551,6 +635,7 @@ def main():
         # video mode (SURVEY 8e option A: contiguous frame ranges, one chain per context): many chains in flight, and one chain alone
         extra["video_8k_chains"] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, "8k", False, min(F, 12), steps=2, temporal=True)
         extra["video_8k_single_chain"] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, "8k", False, 1, steps=4, temporal=True)
+        extra["isp_raw_to_bgr"] = isp_pass(api, torch, dev, local_rank, peak, cpu=not args.no_cpu_baseline)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

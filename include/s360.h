@@ -254,6 +254,12 @@ int s360_isp_process(s360_ctx* ctx, s360_isp* isp, const void* raw, int in_w, in
 int s360_isp_process_dev(s360_ctx* ctx, s360_isp* isp, const void* raw_dev, int in_w, int in_h, int depth_bits, size_t stride_bytes, void* out_dev,
                          int swizzle);
 
+/* The renderer's input straight from a raw frame: an ISP created with 16 output bits (as Unpacker.cpp:174-176 does), its BGR result
+ * narrowed to 8 bits the way the renderer's cv::imread narrows Unpacker's 16-bit PNG (high byte). out_bgr8_dev: (in_h / resize) x
+ * (in_w / resize) x 3 uint8 on the device, ready for s360_render_frame_dev. Asynchronous on the context's stream. */
+int s360_isp_process_frame_dev(s360_ctx* ctx, s360_isp* isp, const void* raw_dev, int in_w, int in_h, int depth_bits, size_t stride_bytes,
+                               uint8_t* out_bgr8_dev);
+
 /* ---- whole frame ---- */
 
 /* renderStereoPanorama (TRSP:716-972) without file I/O. images: one BGR8 image per rig

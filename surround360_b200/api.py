@@ -436,6 +436,10 @@ class CameraIsp:
         _check(lib().s360_isp_process(ctx.h, self.h, C.c_void_p(raw.ctypes.data), w, h, 8 * raw.itemsize, C.c_size_t(raw.strides[0]), _p(out), int(swizzle)))
         return out
 
+    def frameImageDev(self, ctx, raw_dev_ptr, w, h, depth_bits, out_bgr8_dev_ptr, stride_bytes=0):
+        """16-bit ISP result narrowed to the renderer's BGR8 input (high byte, like imread of Unpacker's PNG); device pointers."""
+        _check(lib().s360_isp_process_frame_dev(ctx.h, self.h, C.c_void_p(raw_dev_ptr), w, h, depth_bits, C.c_size_t(stride_bytes), C.c_void_p(out_bgr8_dev_ptr)))
+
     def getImageDev(self, ctx, raw_dev_ptr, w, h, depth_bits, out_dev_ptr, stride_bytes=0, swizzle=True):
         """Device-pointer variant, asynchronous on the context stream (s360_isp_process_dev)."""
         _check(lib().s360_isp_process_dev(ctx.h, self.h, C.c_void_p(raw_dev_ptr), w, h, depth_bits, C.c_size_t(stride_bytes), C.c_void_p(out_dev_ptr), int(swizzle)))

@@ -520,6 +520,14 @@ int s360_isp_process_dev(s360_ctx* c, s360_isp* isp, const void* rawDev, int inW
   isp->pipe.process(c->stream, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8), outDev, swizzle != 0);
   S360_API_END
 }
+int s360_isp_process_frame_dev(s360_ctx* c, s360_isp* isp, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, uint8_t* outBgr8Dev) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(isp != nullptr, "null isp");
+  require(inW > 0 && inH > 0, "bad image size");
+  isp->pipe.process(c->stream, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8), outBgr8Dev, true, true);
+  S360_API_END
+}
 int s360_isp_process(s360_ctx* c, s360_isp* isp, const void* raw, int inW, int inH, int depthBits, size_t strideBytes, void* out, int swizzle) {
   S360_API_BEGIN
   useDevice(c);

@@ -43,7 +43,9 @@ class IspPipeline {
   // loadImage + getImage (CameraIsp.h:831-857, 1275-1299) on device buffers, asynchronous on `st`:
   // raw: inW x inH Bayer samples of depthBits (8 or 16) with strideBytes between rows; out: (inH / resize) x (inW / resize) x 3 of
   // outputBpp bits, tightly packed, BGR when swizzle else RGB.
-  void process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle);
+  // highByte (16-bit ISPs only): store the high byte of every 16-bit sample as uint8 -- what cv::imread(CV_LOAD_IMAGE_COLOR) makes of
+  // the 16-bit PNG the reference's Unpacker writes, i.e. the renderer's input without the PNG round trip.
+  void process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle, bool highByte = false);
 
  private:
   void setup();               // :612-715

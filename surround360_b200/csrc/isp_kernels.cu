@@ -287,7 +287,9 @@ k_isp_iir_columns(const float4* __restrict__ in, int w, int n, float alpha, floa
 
 // sharpenWithIirLowPass (Filter.h:98-130) when `lp` is given, then getImage's conversion (CameraIsp.h:1275-1299): the float -> 8/16
 // bit stores truncate like the reference's implicit conversions; c0/c1/c2 = 2/1/0 when swizzling to BGR
-template <typename T>
+// HIGH8: the 16-bit result narrowed the way cv::imread(CV_LOAD_IMAGE_COLOR) narrows the 16-bit PNG the reference's Unpacker writes
+// (high byte; RigDescription.cpp:97-101 reads what Unpacker.cpp:187-190 wrote) -- the bytes the renderer would load
+template <typename T, bool HIGH8>
 __global__ void __launch_bounds__(256)
 k_isp_finish(const float4* __restrict__ rgb, const float4* __restrict__ lp, size_t n, float aR, float aG, float aB, float noiseCore, float maxVal,
              int swizzle, T* __restrict__ out) {
@@ -306,9 +308,15 @@ k_isp_finish(const float4* __restrict__ rgb, const float4* __restrict__ lp, size
   }
   const int c0 = swizzle ? 2 : 0, c2 = swizzle ? 0 : 2;
   T* o = out + i * 3;
-  o[c0] = (T)(int)p.x;
-  o[1] = (T)(int)p.y;
-  o[c2] = (T)(int)p.z;
+  if (HIGH8) {
+    o[c0] = (T)((int)p.x >> 8);
+    o[1] = (T)((int)p.y >> 8);
+    o[c2] = (T)((int)p.z >> 8);
+  } else {
+    o[c0] = (T)(int)p.x;
+    o[1] = (T)(int)p.y;
+    o[c2] = (T)(int)p.z;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -512,7 +520,8 @@ void IspPipeline::ensureDevice(int w, int h) {
   }
 }
 
-void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle) {
+void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle, bool highByte) {
+  if (highByte && outputBpp_ != 16) throw std::runtime_error("the high-byte output needs an ISP created with 16 output bits");
   if (depthBits != 8 && depthBits != 16) throw std::runtime_error("input is larger that 16 bits per pixel");   // the reference's message, CameraIsp.h:855
   if (!rawDev || !outDev) throw std::runtime_error("null image");
   if (demosaicFilter_ == 1) throw std::runtime_error("the frequency-domain demosaic filter (cv::dct) is not implemented: use 0 (bilinear) or 2 (edge aware)");
@@ -598,8 +607,9 @@ void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH,
     S360_PROF(st, "k_isp_finish", (double)px * ((lp ? 32 : 16) + 3 * (outputBpp_ / 8)));
     const unsigned blocks = (unsigned)((px + 255) / 256);
     const float aR = 1.0f + sharpening_.x, aG = 1.0f + sharpening_.y, aB = 1.0f + sharpening_.z;
-    if (outputBpp_ == 8) k_isp_finish<unsigned char><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned char*>(outDev));
-    else k_isp_finish<unsigned short><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned short*>(outDev));
+    if (highByte) k_isp_finish<unsigned char, true><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned char*>(outDev));
+    else if (outputBpp_ == 8) k_isp_finish<unsigned char, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned char*>(outDev));
+    else k_isp_finish<unsigned short, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned short*>(outDev));
     ++g_launchCount;
   }
   S360_CUDA_CHECK(cudaGetLastError());

@@ -103,3 +103,49 @@ def test_isp_errors(ctx):
         api.CameraIsp(CONFIGS["sensor_a"], 12)
     with pytest.raises(api.VrCamException, match="too small"):
         run_gpu(ctx, "sensor_a", synth.bayer_frame(6, 64, np.uint16, seed=1))
+
+
+def mosaic16(bgr):
+    """A 16-bit GBRG Bayer frame whose photosites sample the given 8-bit BGR image (what a camera of the rig would deliver)."""
+    h, w = bgr.shape[:2]
+    yy, xx = np.mgrid[0:h, 0:w]
+    red = (yy % 2 == 1) & (xx % 2 == 0)
+    blue = (yy % 2 == 0) & (xx % 2 == 1)
+    m = np.where(red, bgr[..., 2], np.where(blue, bgr[..., 0], bgr[..., 1])).astype(np.uint16)
+    return np.ascontiguousarray(m * 160 + 1400)   # above the black level, below saturation
+
+
+def test_raw_to_panorama_on_device(frames17):
+    """The fused chain: 17 raw frames -> s360_isp_process_frame_dev -> s360_render_frame_dev, nothing leaves the device
+    in between. Against the reference's chain: its CameraIsp at 16 bits (what Unpacker writes as PNG), narrowed like the renderer's
+    imread (high byte), rendered from host images."""
+    torch = pytest.importorskip("torch")
+    from test_gpu_frame import SMALL
+    from conftest import RIG17
+    c = api.Context(0)
+    c.load_rig(RIG17)
+    params = api.default_params(**SMALL)
+    raws = [mosaic16(f) for f in frames17]
+    h, w = raws[0].shape
+    isp = api.CameraIsp(CONFIGS["sensor_a"], 16)
+    isp.setBitsPerPixel(16); isp.setDemosaicFilter(2); isp.setResize(1); isp.enableToneMap()
+    d_raw = [torch.from_numpy(r.view(np.int16)).cuda() for r in raws]
+    d_bgr = [torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda") for _ in raws]
+    for r, o in zip(d_raw, d_bgr):
+        isp.frameImageDev(c, r.data_ptr(), w, h, 16, o.data_ptr())
+    eq_w, eq_h, cw, ch = c.output_size(params)
+    d_eq = torch.zeros((eq_h, eq_w, 3), dtype=torch.uint8, device="cuda")
+    d_cube = torch.zeros((ch, cw, 3), dtype=torch.uint8, device="cuda")
+    c.render_frame_dev(params, [o.data_ptr() for o in d_bgr], w, h, d_eq.data_ptr(), d_cube.data_ptr())
+    c.synchronize()
+    # reference chain for the ISP part (3 cameras are enough for the bit check of the narrowing; all 17 feed the host render)
+    host_frames = []
+    for k, r in enumerate(raws):
+        if rb.available() and k in (0, 7, 16):
+            ref16 = run_ref("sensor_a", r, 2, 1, 16)
+            assert np.array_equal(d_bgr[k].cpu().numpy(), (ref16 >> 8).astype(np.uint8)), f"camera {k}"
+        host_frames.append(d_bgr[k].cpu().numpy())
+    eq, cube = c.renderStereoPanorama(params, host_frames)
+    assert np.array_equal(d_eq.cpu().numpy(), eq) and np.array_equal(d_cube.cpu().numpy(), cube)
+    assert eq.std() > 10   # a real picture came out
+    isp.close(); c.close()
