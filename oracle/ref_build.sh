@@ -62,4 +62,8 @@ $CXX $CXXFLAGS $INC -c "$REF/util/JsonUtil.cpp" -o "$OUT/obj/util_JsonUtil.o" &
 $CXX $CXXFLAGS $INC -c "$REF/thirdparty/supereasyjson/json.cpp" -o "$OUT/obj/supereasyjson.o" &
 wait
 $CXX -pthread -shared -o "$OUT/libref_isp.so" "$OUT/obj/ref_isp_capi.o" "$OUT/obj/util_JsonUtil.o" "$OUT/obj/supereasyjson.o" $OBJS -lz
+if [ -f "$REPO/surround360_b200/libs360b200.so" ]; then   # the same library with the GPU adapter of integration/reference_tree/camera_isp compiled in
+  $CXX $CXXFLAGS $INC -I$REF/camera_isp -I$REPO/integration/reference_tree/camera_isp -I$REPO/include -DREF_WITH_B200_ISP -c "$HERE/ref_isp_capi.cpp" -o "$OUT/obj/ref_isp_capi_b200.o"
+  $CXX -pthread -shared -o "$OUT/libref_isp_b200.so" "$OUT/obj/ref_isp_capi_b200.o" "$OUT/obj/util_JsonUtil.o" "$OUT/obj/supereasyjson.o" $OBJS -lz -L"$REPO/surround360_b200" -ls360b200 -Wl,-rpath,'$ORIGIN/../../surround360_b200'
+fi
 echo "ref_build: built $OUT/TestRenderStereoPanorama and $OUT/libref.so"

@@ -10,6 +10,9 @@
 #include <string>
 
 #include "camera_isp/CameraIsp.h"
+#ifdef REF_WITH_B200_ISP
+#include "B200CameraIsp.h"
+#endif
 
 namespace {
 std::string gErr;
@@ -60,6 +63,36 @@ int refisp_process(const char* json, const void* raw, int w, int h, int depthBit
     return 1;
   }
 }
+
+#ifdef REF_WITH_B200_ISP
+// The adapter of integration/reference_tree/camera_isp/B200CameraIsp.h inside the reference build, driven through the reference's
+// base-class interface exactly like Raw2Rgb.cpp:445-456 drives CameraIsp (links the product library, like a maintainer's build).
+int refisp_process_b200(const char* json, const void* raw, int w, int h, int depthBits, int demosaicFilter, int resize, int outputBpp, int toneCurve,
+                        int blackLevelOffset, int swizzle, void* out) {
+  std::lock_guard<std::mutex> lock(gMutex);
+  try {
+    google::refShimMinLogLevel() = 1;
+    B200CameraIsp isp(json, outputBpp);
+    isp.setBitsPerPixel(16);
+    isp.setDemosaicFilter(demosaicFilter);
+    isp.setResize(resize);
+    if (toneCurve) isp.enableToneMap(); else isp.disableToneMap();
+    isp.addBlackLevelOffset(blackLevelOffset);
+    cv::Mat input(h, w, depthBits == 8 ? CV_8U : CV_16U);
+    std::memcpy(input.data, raw, (size_t)w * h * (depthBits == 8 ? 1 : 2));
+    CameraIsp* base = &isp;   // the pixel path goes through the virtual members
+    base->loadImage(input);
+    const int ow = w / resize, oh = h / resize;
+    cv::Mat output(oh, ow, outputBpp == 8 ? CV_8UC3 : CV_16UC3);
+    base->getImage(output, swizzle != 0);
+    std::memcpy(out, output.data, (size_t)ow * oh * 3 * (outputBpp == 8 ? 1 : 2));
+    return 0;
+  } catch (const std::exception& e) {
+    gErr = e.what();
+    return 1;
+  }
+}
+#endif
 
 // the tables of setup(): compositeCCM (9 floats, row major), toneCurveLut (4096 x 3 floats), vignette gains of every column / row
 // (w x 3, h x 3) for an image of w x h after the resize

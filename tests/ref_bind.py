@@ -258,3 +258,23 @@ def isp_tables(json_text, w, h, output_bpp=8, tone_curve=True):
     if L.refisp_tables(json_text.encode(), output_bpp, int(tone_curve), w, h, P(ccm), P(lut), P(vh), P(vv)):
         raise RuntimeError(L.refisp_last_error().decode())
     return ccm, lut, vh, vv
+
+
+REF_ISP_B200_SO = os.path.join(ORACLE_DIR, "_ref", "libref_isp_b200.so")
+_IBLIB = None
+
+
+def isp_process_b200(json_text, raw, demosaic_filter=2, resize=1, output_bpp=8, tone_curve=True, black_level_offset=0, swizzle=True):
+    """The same call sequence inside the reference build, but on the adapter of integration/reference_tree/camera_isp/B200CameraIsp.h
+    (the reference's CameraIsp interface, pixels on the GPU through include/s360.h)."""
+    global _IBLIB
+    if _IBLIB is None:
+        _IBLIB = C.CDLL(REF_ISP_B200_SO)
+        _IBLIB.refisp_last_error.restype = C.c_char_p
+    raw = np.ascontiguousarray(raw)
+    h, w = raw.shape
+    out = np.zeros((h // resize, w // resize, 3), np.uint8 if output_bpp == 8 else np.uint16)
+    if _IBLIB.refisp_process_b200(json_text.encode(), P(raw), w, h, 8 if raw.dtype == np.uint8 else 16, demosaic_filter, resize, output_bpp,
+                                  int(tone_curve), black_level_offset, int(swizzle), P(out)):
+        raise RuntimeError(_IBLIB.refisp_last_error().decode())
+    return out

@@ -149,3 +149,16 @@ def test_raw_to_panorama_on_device(frames17):
     assert np.array_equal(d_eq.cpu().numpy(), eq) and np.array_equal(d_cube.cpu().numpy(), cube)
     assert eq.std() > 10   # a real picture came out
     isp.close(); c.close()
+
+
+@pytest.mark.skipif(not os.path.exists(rb.REF_ISP_B200_SO), reason="oracle/_ref/libref_isp_b200.so not built")
+def test_reference_build_with_b200_isp_adapter():
+    """integration/reference_tree/camera_isp/B200CameraIsp.h compiled INTO the reference build and driven through the reference's
+    CameraIsp interface (virtual loadImage / getImage, the setters of Raw2Rgb.cpp:446-454): same bytes as the reference's own class."""
+    raw = synth.bayer_frame(136, 200, np.uint16, seed=21)
+    for dm, rs, bpp, tone, off, sw in ((2, 1, 16, True, 0, True), (0, 2, 8, False, 12, False)):
+        a = rb.isp_process_b200(CONFIGS["sensor_a"], raw, dm, rs, bpp, tone, off, sw)
+        b = rb.isp_process(CONFIGS["sensor_a"], raw, dm, rs, bpp, tone, off, sw)
+        assert np.array_equal(a, b)
+    with pytest.raises(RuntimeError, match="frequency"):
+        rb.isp_process_b200(CONFIGS["sensor_a"], raw, 1)
