@@ -335,9 +335,10 @@ def isp_pass(api, torch, dev, local_rank, peak, cpu=True):
     outs = [torch.empty((h, w, 3), dtype=torch.uint8, device=dev) for _ in range(n_cam)]
     st = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
-    def frame():
-        for r, o in zip(raws, outs):
-            isp.frameImageDev(ctx, r.data_ptr(), w, h, 16, o.data_ptr())
+    rp, op = [r.data_ptr() for r in raws], [o.data_ptr() for o in outs]
+
+    def frame():   # the 17 cameras through shared launches (s360_isp_process_frames_dev)
+        isp.frameImagesDev(ctx, rp, w, h, 16, op)
     for _ in range(3):
         frame()
     ctx.synchronize()
@@ -363,7 +364,7 @@ def isp_pass(api, torch, dev, local_rank, peak, cpu=True):
     ctx.profile_enable(0)
     isp.close(); ctx.close()
     res = {"workload": "17 raw 2048x2048 uint16 GBRG frames -> BGR8 (edge-aware demosaic, CCM + tone curve, IIR unsharp mask), inputs and outputs resident in HBM",
-           "ms_per_rig_frame": ms, "raw_mp_per_s": n_cam * w * h / 1e6 / (ms / 1e3), "rig_frames_per_s": 1000.0 / ms, "launches_per_rig_frame": 10 * n_cam,
+           "ms_per_rig_frame": ms, "raw_mp_per_s": n_cam * w * h / 1e6 / (ms / 1e3), "rig_frames_per_s": 1000.0 / ms, "launches_per_rig_frame": 10,
            "output_crc32_cam0": crc, "kernels": sorted(kern, key=lambda k: -k["ms_per_frame_alone"])}
     if cpu and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_isp.so")):
         r = subprocess.run([sys.executable, "-c", ISP_CPU_SNIPPET % (os.path.join(ROOT, "tests"), ROOT, cfg)], capture_output=True, text=True, timeout=600)

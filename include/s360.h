@@ -222,8 +222,8 @@ int s360_pole_to_side(s360_ctx* ctx, const s360_params* p, const uint8_t* side_b
 /* TestHyperPreview (source/test/TestHyperPreview.cpp:77-185): the fast mono preview straight from the raw Bayer frames (uint16,
  * img_w x img_h each) of the top, bottom and secondary-bottom cameras of the loaded rig: 2x2 demosaic, alpha fades, cubic
  * projection through the precomputed equirect->camera warp (built on the first call for a size, then resident), softmax flatten,
- * x 255/65535. out_bgr: eqr_h x eqr_w x 3 float32, the image the reference hands to imwrite. Float path: within 1e-5 relative of
- * the CPU result (device expf), not bit-identical. */
+ * x 255/65535. out_bgr: eqr_h x eqr_w x 3 float32, the image the reference hands to imwrite. Bit-identical to the reference build
+ * for gamma == 1 (its default; the blend's expf is an exact port of the host's); gamma != 1 goes through the device's powf (2e-4). */
 int s360_hyper_preview(s360_ctx* ctx, const uint16_t* raw_top, const uint16_t* raw_bottom, const uint16_t* raw_bottom2, int img_w, int img_h,
                        int eqr_w, int eqr_h, double gamma, double softmax_coef, float* out_bgr);
 
@@ -259,6 +259,10 @@ int s360_isp_process_dev(s360_ctx* ctx, s360_isp* isp, const void* raw_dev, int 
  * (in_w / resize) x 3 uint8 on the device, ready for s360_render_frame_dev. Asynchronous on the context's stream. */
 int s360_isp_process_frame_dev(s360_ctx* ctx, s360_isp* isp, const void* raw_dev, int in_w, int in_h, int depth_bits, size_t stride_bytes,
                                uint8_t* out_bgr8_dev);
+
+/* The same for the n cameras of a frame (n <= 32, one size) through shared launches: pointer arrays on the HOST, images on the device. */
+int s360_isp_process_frames_dev(s360_ctx* ctx, s360_isp* isp, int n, const void* const* raw_dev, int in_w, int in_h, int depth_bits,
+                                size_t stride_bytes, uint8_t* const* out_bgr8_dev);
 
 /* ---- whole frame ---- */
 

@@ -440,6 +440,12 @@ class CameraIsp:
         """16-bit ISP result narrowed to the renderer's BGR8 input (high byte, like imread of Unpacker's PNG); device pointers."""
         _check(lib().s360_isp_process_frame_dev(ctx.h, self.h, C.c_void_p(raw_dev_ptr), w, h, depth_bits, C.c_size_t(stride_bytes), C.c_void_p(out_bgr8_dev_ptr)))
 
+    def frameImagesDev(self, ctx, raw_dev_ptrs, w, h, depth_bits, out_bgr8_dev_ptrs, stride_bytes=0):
+        """The cameras of one frame in shared launches (s360_isp_process_frames_dev)."""
+        n = len(raw_dev_ptrs)
+        a = (C.c_void_p * n)(*[int(p) for p in raw_dev_ptrs]); b = (C.c_void_p * n)(*[int(p) for p in out_bgr8_dev_ptrs])
+        _check(lib().s360_isp_process_frames_dev(ctx.h, self.h, n, a, w, h, depth_bits, C.c_size_t(stride_bytes), b))
+
     def getImageDev(self, ctx, raw_dev_ptr, w, h, depth_bits, out_dev_ptr, stride_bytes=0, swizzle=True):
         """Device-pointer variant, asynchronous on the context stream (s360_isp_process_dev)."""
         _check(lib().s360_isp_process_dev(ctx.h, self.h, C.c_void_p(raw_dev_ptr), w, h, depth_bits, C.c_size_t(stride_bytes), C.c_void_p(out_dev_ptr), int(swizzle)))

@@ -528,6 +528,16 @@ int s360_isp_process_frame_dev(s360_ctx* c, s360_isp* isp, const void* rawDev, i
   isp->pipe.process(c->stream, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8), outBgr8Dev, true, true);
   S360_API_END
 }
+int s360_isp_process_frames_dev(s360_ctx* c, s360_isp* isp, int n, const void* const* rawDev, int inW, int inH, int depthBits, size_t strideBytes,
+                                uint8_t* const* outBgr8Dev) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(isp != nullptr && rawDev && outBgr8Dev, "null argument");
+  require(inW > 0 && inH > 0, "bad image size");
+  isp->pipe.processBatch(c->stream, n, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8),
+                         reinterpret_cast<void* const*>(outBgr8Dev), true, true);
+  S360_API_END
+}
 int s360_isp_process(s360_ctx* c, s360_isp* isp, const void* raw, int inW, int inH, int depthBits, size_t strideBytes, void* out, int swizzle) {
   S360_API_BEGIN
   useDevice(c);

@@ -46,11 +46,15 @@ class IspPipeline {
   // highByte (16-bit ISPs only): store the high byte of every 16-bit sample as uint8 -- what cv::imread(CV_LOAD_IMAGE_COLOR) makes of
   // the 16-bit PNG the reference's Unpacker writes, i.e. the renderer's input without the PNG round trip.
   void process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle, bool highByte = false);
+  // n images of one size through the same launches (blockIdx.z / .y = image): the rig's 17 cameras per frame. The IIR passes have
+  // only one thread per image line, so batching is what fills the GPU there.
+  void processBatch(cudaStream_t st, int n, const void* const* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* const* outDev, bool swizzle,
+                    bool highByte = false);
 
  private:
   void setup();               // :612-715
   void buildToneCurveLut();   // :390-425
-  void ensureDevice(int w, int h);
+  void ensureDevice(int w, int h, int n);
 
   // configuration (CameraIsp's members)
   std::string bayerPattern_;

@@ -3,55 +3,12 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include "expf_bits.cuh"
 #include "isp.h"
 #include "json_mini.h"
 #include "kernels.h"
 
 namespace s360 {
-
-// ------------------------------------------------------------------------------------------------------------------------------
-// expf with the bits of the C library (glibc >= 2.27, sysdeps/ieee754/flt-32/e_expf.c: Szabolcs Nagy's exp2f-table algorithm --
-// double arithmetic, 32-entry table, one final rounding to float). The unsharp mask's noise coring evaluates expf on arbitrary
-// floats (CameraIsp.h:1244-1259 -> Filter.h:112-118); CUDA's expf may differ from the host's in the last place, which the 8/16-bit
-// truncation after it turns into rare 1-LSB differences. The same IEEE double operations give the same bits on the device.
-// Table: T[i] = bits(2^(i/32)) - (i << 47); pinned against the host's expf in tests/test_isp_tables.py.
-// ------------------------------------------------------------------------------------------------------------------------------
-static __device__ const unsigned long long kExp2fTab[32] = {
-    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull, 0x3fef54873168b9aaull,
-    0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
-    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull,
-    0x3feea11473eb0187ull, 0x3feea589994cce13ull, 0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
-    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
-    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
-__device__ __forceinline__ float expfHostBits(float x) {
-  const unsigned ux = __float_as_uint(x);
-  const unsigned abstop = (ux >> 20) & 0x7ffu;
-  if (abstop >= 0x42bu) {                                            // |x| >= 88 or NaN
-    if (ux == 0xff800000u) return 0.0f;
-    if (abstop >= 0x7f8u) return x + x;
-    if (x > __uint_as_float(0x42b17217u)) return __uint_as_float(0x7f800000u);   // x > log(2^128): overflow
-    if (x < __uint_as_float(0xc2cff1b4u)) return 0.0f;                           // x < log(2^-150): underflow
-  }
-  const double invLn2N = __longlong_as_double(0x40471547652b82feLL);             // 0x1.71547652b82fep+0 * 32
-  const double shift = __longlong_as_double(0x4338000000000000LL);               // 0x1.8p+52
-  const double c0 = __longlong_as_double(0x3ebc6af84b912394LL);                  // 0x1.c6af84b912394p-5 / 32^3
-  const double c1 = __longlong_as_double(0x3f2ebfce50fac4f3LL);                  // 0x1.ebfce50fac4f3p-3 / 32^2
-  const double c2 = __longlong_as_double(0x3f962e42ff0c52d6LL);                  // 0x1.62e42ff0c52d6p-1 / 32
-  const double z = invLn2N * (double)x;
-  double kd = z + shift;
-  const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
-  kd = kd - shift;
-  const double r = z - kd;
-  unsigned long long t = kExp2fTab[ki & 31u];
-  t += ki << 47;
-  const double s = __longlong_as_double((long long)t);
-  const double zz = c0 * r + c1;
-  const double r2 = r * r;
-  double y = c2 * r + 1.0;
-  y = zz * r2 + y;
-  y = y * s;
-  return (float)y;
-}
 
 // ------------------------------------------------------------------------------------------------------------------------------
 struct IspDev {
@@ -62,6 +19,8 @@ struct IspDev {
   float ccm[9];              // compositeCCM, row major
   float maxVal;
 };
+constexpr int kIspMaxBatch = 32;   // images of one size and configuration per launch (the rig has 17 cameras)
+struct IspBatch { const void* raw[kIspMaxBatch]; void* out[kIspMaxBatch]; size_t strideBytes; };
 __device__ __forceinline__ int ispReflect(int x, int r) { return x < 0 ? -x : x >= r ? 2 * r - x - 2 : x; }   // MathUtil.h:41-44
 __device__ __forceinline__ float ispClamp(float x, float a, float b) { return x < a ? a : x > b ? b : x; }    // MathUtil.h:36-39
 __device__ __forceinline__ int ispChan(const IspDev& P, int i, int j) { return P.chan[(i & 1) * 2 + (j & 1)]; }
@@ -70,9 +29,12 @@ __device__ __forceinline__ int ispChan(const IspDev& P, int i, int j) { return P
 // + clampAndStretch (:1128-1143): raw samples -> the float Bayer plane the demosaic reads
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_isp_prep(const T* __restrict__ in, size_t strideBytes, IspDev P, const float* __restrict__ vigH, const float* __restrict__ vigV, float* __restrict__ raw) {
+k_isp_prep(IspBatch B, IspDev P, const float* __restrict__ vigH, const float* __restrict__ vigV, float* __restrict__ rawAll) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= P.w || i >= P.h) return;
+  const T* __restrict__ in = reinterpret_cast<const T*>(B.raw[blockIdx.z]);
+  const size_t strideBytes = B.strideBytes;
+  float* __restrict__ raw = rawAll + (size_t)blockIdx.z * P.w * P.h;
   const int r = P.resize > 1 ? 2 : 1;
   float sum = 0.0f;
   for (int k = 0; k < P.resize; ++k) {
@@ -113,10 +75,13 @@ __device__ __forceinline__ bool ispRedGreenRow(const IspDev& P, int i) {   // Ca
 // demosaicBilinearFilter (CameraIsp.h:89-148) + colorCorrect. Every neighbour the reference reads from its r / g / b planes is a
 // position where that plane holds the raw sample (reflect keeps the Bayer parity), so the raw plane is read directly.
 __global__ void __launch_bounds__(256)
-k_isp_demosaic_bilinear(const float* __restrict__ raw, IspDev P, const float* __restrict__ lut, float4* __restrict__ rgb) {
+k_isp_demosaic_bilinear(const float* __restrict__ rawAll, IspDev P, const float* __restrict__ lut, float4* __restrict__ rgbAll) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= P.w || i >= P.h) return;
   const int w = P.w, h = P.h;
+  const size_t img = (size_t)blockIdx.z * w * h;
+  const float* __restrict__ raw = rawAll + img;
+  float4* __restrict__ rgb = rgbAll + img;
   const int i_1 = ispReflect(i - 1, h), i1 = ispReflect(i + 1, h), j_1 = ispReflect(j - 1, w), j1 = ispReflect(j + 1, w);
   auto R = [&](int y, int x) { return __ldg(raw + (size_t)y * w + x); };
   const int ch = ispChan(P, i, j);
@@ -145,10 +110,15 @@ k_isp_demosaic_bilinear(const float* __restrict__ raw, IspDev P, const float* __
 // demosaicEdgeAware, first loop (CameraIsp.h:191-230): vertical / horizontal green estimates and their gradients; the flag is the
 // term the homogeneity test counts (dH <= dV)
 __global__ void __launch_bounds__(256)
-k_isp_green_candidates(const float* __restrict__ raw, IspDev P, float* __restrict__ gV, float* __restrict__ gH, unsigned char* __restrict__ flag) {
+k_isp_green_candidates(const float* __restrict__ rawAll, IspDev P, float* __restrict__ gVAll, float* __restrict__ gHAll, unsigned char* __restrict__ flagAll) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= P.w || i >= P.h) return;
   const int w = P.w, h = P.h;
+  const size_t img = (size_t)blockIdx.z * w * h;
+  const float* __restrict__ raw = rawAll + img;
+  float* __restrict__ gV = gVAll + img;
+  float* __restrict__ gH = gHAll + img;
+  unsigned char* __restrict__ flag = flagAll + img;
   const int i_1 = ispReflect(i - 1, h), i1 = ispReflect(i + 1, h), i_2 = ispReflect(i - 2, h), i2 = ispReflect(i + 2, h);
   const int j_1 = ispReflect(j - 1, w), j1 = ispReflect(j + 1, w), j_2 = ispReflect(j - 2, w), j2 = ispReflect(j + 2, w);
   auto R = [&](int y, int x) { return __ldg(raw + (size_t)y * w + x); };
@@ -180,10 +150,17 @@ k_isp_green_candidates(const float* __restrict__ raw, IspDev P, float* __restric
 // second and third loop (CameraIsp.h:231-262): 9 x 9 homogeneity vote picks the green estimate; red - green / blue - green at
 // the red / blue sites. The block stages the votes of its 8 x 32 pixels plus a 4-pixel apron (reflected indices) in shared memory.
 __global__ void __launch_bounds__(256)
-k_isp_green_select(const float* __restrict__ raw, const float* __restrict__ gV, const float* __restrict__ gH, const unsigned char* __restrict__ flag,
-                   IspDev P, float* __restrict__ green, float* __restrict__ diff) {
+k_isp_green_select(const float* __restrict__ rawAll, const float* __restrict__ gVAll, const float* __restrict__ gHAll, const unsigned char* __restrict__ flagAll,
+                   IspDev P, float* __restrict__ greenAll, float* __restrict__ diffAll) {
   __shared__ unsigned char sm[16][40];
   const int w = P.w, h = P.h;
+  const size_t img = (size_t)blockIdx.z * w * h;
+  const float* __restrict__ raw = rawAll + img;
+  const float* __restrict__ gV = gVAll + img;
+  const float* __restrict__ gH = gHAll + img;
+  const unsigned char* __restrict__ flag = flagAll + img;
+  float* __restrict__ green = greenAll + img;
+  float* __restrict__ diff = diffAll + img;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
   for (int t = threadIdx.y * 32 + threadIdx.x; t < 16 * 40; t += 256) {
     const int ty = t / 40, tx = t - ty * 40;
@@ -207,10 +184,14 @@ k_isp_green_select(const float* __restrict__ raw, const float* __restrict__ gV, 
 // last loop (CameraIsp.h:263-335): constant-hue interpolation of red and blue from the colour differences, then colorCorrect.
 // The sums keep the reference's terms and order, including the repeated (i1, j2) term of the six-tap average.
 __global__ void __launch_bounds__(256)
-k_isp_demosaic_edge_aware(const float* __restrict__ green, const float* __restrict__ diff, IspDev P, const float* __restrict__ lut, float4* __restrict__ rgb) {
+k_isp_demosaic_edge_aware(const float* __restrict__ greenAll, const float* __restrict__ diffAll, IspDev P, const float* __restrict__ lut, float4* __restrict__ rgbAll) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= P.w || i >= P.h) return;
   const int w = P.w, h = P.h;
+  const size_t img = (size_t)blockIdx.z * w * h;
+  const float* __restrict__ green = greenAll + img;
+  const float* __restrict__ diff = diffAll + img;
+  float4* __restrict__ rgb = rgbAll + img;
   const int i_1 = ispReflect(i - 1, h), i1 = ispReflect(i + 1, h), i_2 = ispReflect(i - 2, h), i2 = ispReflect(i + 2, h);
   const int j_1 = ispReflect(j - 1, w), j1 = ispReflect(j + 1, w), j_2 = ispReflect(j - 2, w), j2 = ispReflect(j + 2, w);
   auto D = [&](int y, int x) { return __ldg(diff + (size_t)y * w + x); };
@@ -230,8 +211,10 @@ k_isp_demosaic_edge_aware(const float* __restrict__ green, const float* __restri
 }
 
 // 32 x 32 tile transpose of 16-byte pixels (the horizontal IIR pass runs along columns of the transposed image)
-__global__ void k_isp_transpose(const float4* __restrict__ src, int w, int h, float4* __restrict__ dst) {
+__global__ void k_isp_transpose(const float4* __restrict__ srcAll, int w, int h, float4* __restrict__ dstAll) {
   __shared__ float4 tile[32][33];
+  const float4* __restrict__ src = srcAll + (size_t)blockIdx.z * w * h;
+  float4* __restrict__ dst = dstAll + (size_t)blockIdx.z * w * h;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int x = bx + threadIdx.x, y = by + r;
@@ -245,43 +228,60 @@ __global__ void k_isp_transpose(const float4* __restrict__ src, int w, int h, fl
 }
 
 // One pass of iirLowPass<ReflectBoundary, ReflectBoundary, Vec3f> (Filter.h:38-96) along the columns of a w-wide, n-tall image:
-// causal sweep into `buf`, anticausal sweep out of it, clamped to [0, maxVal]. One thread per column; the loads of the next
-// kBatch rows are issued together ahead of the dependent lerps (v = ip * (1 - alpha) + v * alpha per channel).
+// causal sweep into `buf`, anticausal sweep out of it, clamped to [0, maxVal]. One thread per column and image (blockIdx.y); the
+// recurrence v = ip * (1 - alpha) + v * alpha is sequential by definition, so the rows are fetched kIspIirBatch at a time and the
+// loads of the NEXT batch are in flight while the dependent lerps of the current one execute (a step would otherwise expose a full
+// memory round trip).
 constexpr int kIspIirBatch = 8;
 __global__ void __launch_bounds__(128)
-k_isp_iir_columns(const float4* __restrict__ in, int w, int n, float alpha, float maxVal, float4* __restrict__ buf, float4* __restrict__ out) {
+k_isp_iir_columns(const float4* __restrict__ inAll, int w, int n, float alpha, float maxVal, float4* __restrict__ bufAll, float4* __restrict__ outAll) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
+  const size_t img = (size_t)blockIdx.y * w * n;
+  const float4* __restrict__ in = inAll + img;
+  float4* __restrict__ buf = bufAll + img;
+  float4* __restrict__ out = outAll + img;
   const float om = 1.0f - alpha;
   const float4 p0 = in[x];
   float v0 = p0.x, v1 = p0.y, v2 = p0.z;
+  float4 cur[kIspIirBatch], nxt[kIspIirBatch];
+  // causal: j = 1..n reads row reflect(j), writes buffer row j - 1
+#pragma unroll
+  for (int u = 0; u < kIspIirBatch; ++u)
+    if (1 + u <= n) cur[u] = in[(size_t)ispReflect(1 + u, n) * w + x];
   for (int j0 = 1; j0 <= n; j0 += kIspIirBatch) {
-    float4 ip[kIspIirBatch];
 #pragma unroll
     for (int u = 0; u < kIspIirBatch; ++u)
-      if (j0 + u <= n) ip[u] = in[(size_t)ispReflect(j0 + u, n) * w + x];
+      if (j0 + kIspIirBatch + u <= n) nxt[u] = in[(size_t)ispReflect(j0 + kIspIirBatch + u, n) * w + x];
 #pragma unroll
     for (int u = 0; u < kIspIirBatch; ++u)
       if (j0 + u <= n) {
-        v0 = ip[u].x * om + v0 * alpha;
-        v1 = ip[u].y * om + v1 * alpha;
-        v2 = ip[u].z * om + v2 * alpha;
-        buf[(size_t)ispReflect(j0 + u - 1, n) * w + x] = make_float4(v0, v1, v2, 0.0f);
+        v0 = cur[u].x * om + v0 * alpha;
+        v1 = cur[u].y * om + v1 * alpha;
+        v2 = cur[u].z * om + v2 * alpha;
+        buf[(size_t)(j0 + u - 1) * w + x] = make_float4(v0, v1, v2, 0.0f);
       }
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u) cur[u] = nxt[u];
   }
+  // anticausal: j = n-2..-1 reads buffer row reflect(j), writes row j + 1. The first batch reads rows this thread wrote last.
+#pragma unroll
+  for (int u = 0; u < kIspIirBatch; ++u)
+    if (n - 2 - u >= -1) cur[u] = buf[(size_t)ispReflect(n - 2 - u, n) * w + x];
   for (int j0 = n - 2; j0 >= -1; j0 -= kIspIirBatch) {
-    float4 ip[kIspIirBatch];
 #pragma unroll
     for (int u = 0; u < kIspIirBatch; ++u)
-      if (j0 - u >= -1) ip[u] = buf[(size_t)ispReflect(j0 - u, n) * w + x];
+      if (j0 - kIspIirBatch - u >= -1) nxt[u] = buf[(size_t)ispReflect(j0 - kIspIirBatch - u, n) * w + x];
 #pragma unroll
     for (int u = 0; u < kIspIirBatch; ++u)
       if (j0 - u >= -1) {
-        v0 = ip[u].x * om + v0 * alpha;
-        v1 = ip[u].y * om + v1 * alpha;
-        v2 = ip[u].z * om + v2 * alpha;
+        v0 = cur[u].x * om + v0 * alpha;
+        v1 = cur[u].y * om + v1 * alpha;
+        v2 = cur[u].z * om + v2 * alpha;
         out[(size_t)(j0 - u + 1) * w + x] = make_float4(ispClamp(v0, 0.0f, maxVal), ispClamp(v1, 0.0f, maxVal), ispClamp(v2, 0.0f, maxVal), 0.0f);
       }
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u) cur[u] = nxt[u];
   }
 }
 
@@ -292,12 +292,14 @@ k_isp_iir_columns(const float4* __restrict__ in, int w, int n, float alpha, floa
 template <typename T, bool HIGH8>
 __global__ void __launch_bounds__(256)
 k_isp_finish(const float4* __restrict__ rgb, const float4* __restrict__ lp, size_t n, float aR, float aG, float aB, float noiseCore, float maxVal,
-             int swizzle, T* __restrict__ out) {
+             int swizzle, IspBatch B) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float4 p = rgb[i];
+  const size_t g = (size_t)blockIdx.y * n + i;   // pixel i of image blockIdx.y
+  T* __restrict__ out = reinterpret_cast<T*>(B.out[blockIdx.y]);
+  float4 p = rgb[g];
   if (lp) {
-    const float4 l = lp[i];
+    const float4 l = lp[g];
     const float h0 = p.x - l.x, h1 = p.y - l.y, h2 = p.z - l.z;
     const float n0 = 1.0f - expfHostBits(-(h0 * h0 * noiseCore));
     const float n1 = 1.0f - expfHostBits(-(h1 * h1 * noiseCore));
@@ -501,10 +503,11 @@ IspPipeline::~IspPipeline() {
   if (dWork_) cudaFree(dWork_);
 }
 
-// per pixel: rgb, tA, tB float4 (48 B) + scratch float4 (16 B); the demosaic's temporaries (raw, gV, gH, green, diff: 5 floats, and
-// one flag byte) live in tA / tB / scratch, which the sharpen stage only needs afterwards
-void IspPipeline::ensureDevice(int w, int h) {
-  const size_t px = (size_t)w * h, need = px * 64;
+// per pixel and image: rgb, tA, tB float4 (48 B) + scratch float4 (16 B); the demosaic's temporaries (raw, gV, gH, green, diff: 5
+// floats, and one flag byte) live in tA / tB / scratch, which the sharpen stage only needs afterwards. Every array holds the n images
+// of a batch back to back.
+void IspPipeline::ensureDevice(int w, int h, int n) {
+  const size_t px = (size_t)w * h, need = px * 64 * n;
   if (need > workBytes_) {
     if (dWork_) S360_CUDA_CHECK(cudaFree(dWork_));
     dWork_ = nullptr; workBytes_ = 0;
@@ -521,9 +524,16 @@ void IspPipeline::ensureDevice(int w, int h) {
 }
 
 void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle, bool highByte) {
+  processBatch(st, 1, &rawDev, inW, inH, depthBits, strideBytes, &outDev, swizzle, highByte);
+}
+
+void IspPipeline::processBatch(cudaStream_t st, int n, const void* const* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* const* outDev,
+                               bool swizzle, bool highByte) {
+  if (n < 1 || n > kIspMaxBatch) throw std::runtime_error("ISP batch size out of range (1.." + std::to_string(kIspMaxBatch) + ")");
   if (highByte && outputBpp_ != 16) throw std::runtime_error("the high-byte output needs an ISP created with 16 output bits");
   if (depthBits != 8 && depthBits != 16) throw std::runtime_error("input is larger that 16 bits per pixel");   // the reference's message, CameraIsp.h:855
   if (!rawDev || !outDev) throw std::runtime_error("null image");
+  for (int k = 0; k < n; ++k) if (!rawDev[k] || !outDev[k]) throw std::runtime_error("null image");
   if (demosaicFilter_ == 1) throw std::runtime_error("the frequency-domain demosaic filter (cv::dct) is not implemented: use 0 (bilinear) or 2 (edge aware)");
   if (stuckPixelRadius_ > 0 && stuckPixelThreshold_ <= 1)
     throw std::runtime_error("stuck-pixel removal with stuckPixelThreshold <= 1 is a sequential in-place scan and is not implemented");
@@ -535,7 +545,7 @@ void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH,
   // loadImage: the input depth overrides bitsPerPixel; only the 16-bit case recomputes maxPixelValue (CameraIsp.h:843-853)
   if (depthBits == 8) bitsPerPixel_ = 8;
   else { bitsPerPixel_ = 16; maxPixelValue_ = (1 << bitsPerPixel_) - 1; }
-  ensureDevice(w, h);
+  ensureDevice(w, h, n);
   if (lutDirty_) {
     S360_CUDA_CHECK(cudaMemcpyAsync(dLut_, toneCurveLut_.data(), toneCurveLut_.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     S360_CUDA_CHECK(cudaStreamSynchronize(st));   // the host vector may be rebuilt right after the call
@@ -562,54 +572,58 @@ void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH,
   for (int k = 0; k < 4; ++k) P.chan[k] = redBayerPixel_[k / 2][k % 2] ? 0 : greenBayerPixel_[k / 2][k % 2] ? 1 : 2;
   std::memcpy(P.ccm, compositeCCM_, sizeof P.ccm);
   P.maxVal = (1 << outputBpp_) - 1.0f;   // sharpen(), CameraIsp.h:1248
+  IspBatch B;
+  std::memset(&B, 0, sizeof B);
+  for (int k = 0; k < n; ++k) { B.raw[k] = rawDev[k]; B.out[k] = outDev[k]; }
+  B.strideBytes = strideBytes;
 
-  const size_t px = (size_t)w * h;
+  const size_t px = (size_t)w * h, all = px * n;
   float4* rgb = reinterpret_cast<float4*>(dWork_);
-  float4* tA = rgb + px;
-  float4* tB = tA + px;
-  float4* scratch = tB + px;
+  float4* tA = rgb + all;
+  float4* tB = tA + all;
+  float4* scratch = tB + all;
   float* raw = reinterpret_cast<float*>(tA);         // demosaic temporaries, dead before the sharpen stage writes tA / tB / scratch
-  float* gV = raw + px;
-  float* gH = gV + px;
-  float* green = gH + px;
+  float* gV = raw + all;
+  float* gH = gV + all;
+  float* green = gH + all;
   float* diff = reinterpret_cast<float*>(tB);
   unsigned char* flag = reinterpret_cast<unsigned char*>(scratch);
   const float* vigH = dVig_;
   const float* vigV = dVig_ + (size_t)w * 3;
-  const dim3 b(32, 8), g(iDivUp(w, 32), iDivUp(h, 8));
+  const dim3 b(32, 8), g(iDivUp(w, 32), iDivUp(h, 8), n);
   {
-    S360_PROF(st, "k_isp_prep", (double)px * (depthBits / 8) * resize_ * resize_ + (double)px * 4);
-    if (depthBits == 8) k_isp_prep<unsigned char><<<g, b, 0, st>>>(reinterpret_cast<const unsigned char*>(rawDev), strideBytes, P, vigH, vigV, raw);
-    else k_isp_prep<unsigned short><<<g, b, 0, st>>>(reinterpret_cast<const unsigned short*>(rawDev), strideBytes, P, vigH, vigV, raw);
+    S360_PROF(st, "k_isp_prep", (double)all * (depthBits / 8) * resize_ * resize_ + (double)all * 4);
+    if (depthBits == 8) k_isp_prep<unsigned char><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
+    else k_isp_prep<unsigned short><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
   }
   if (demosaicFilter_ == 0) {
-    S360_PROF(st, "k_isp_demosaic_bilinear", (double)px * (4 + 16));
+    S360_PROF(st, "k_isp_demosaic_bilinear", (double)all * (4 + 16));
     k_isp_demosaic_bilinear<<<g, b, 0, st>>>(raw, P, dLut_, rgb);
     g_launchCount += 2;
   } else {
-    { S360_PROF(st, "k_isp_green_candidates", (double)px * (4 + 9)); k_isp_green_candidates<<<g, b, 0, st>>>(raw, P, gV, gH, flag); }
-    { S360_PROF(st, "k_isp_green_select", (double)px * (13 + 8)); k_isp_green_select<<<g, b, 0, st>>>(raw, gV, gH, flag, P, green, diff); }
-    { S360_PROF(st, "k_isp_demosaic_edge_aware", (double)px * (8 + 16)); k_isp_demosaic_edge_aware<<<g, b, 0, st>>>(green, diff, P, dLut_, rgb); }
+    { S360_PROF(st, "k_isp_green_candidates", (double)all * (4 + 9)); k_isp_green_candidates<<<g, b, 0, st>>>(raw, P, gV, gH, flag); }
+    { S360_PROF(st, "k_isp_green_select", (double)all * (13 + 8)); k_isp_green_select<<<g, b, 0, st>>>(raw, gV, gH, flag, P, green, diff); }
+    { S360_PROF(st, "k_isp_demosaic_edge_aware", (double)all * (8 + 16)); k_isp_demosaic_edge_aware<<<g, b, 0, st>>>(green, diff, P, dLut_, rgb); }
     g_launchCount += 4;
   }
   const float4* lp = nullptr;
   if (sharpening_.x != 0.0 && sharpening_.y != 0.0 && sharpening_.z != 0.0) {   // sharpen(), CameraIsp.h:1244-1259
     const float alpha = powf(sharpeningSupport_, 1.0f / 4.0f);                  // Filter.h:46
     const dim3 tb(32, 8);
-    { S360_PROF(st, "k_isp_transpose", (double)px * 32); k_isp_transpose<<<dim3(iDivUp(w, 32), iDivUp(h, 32)), tb, 0, st>>>(rgb, w, h, tA); }             // tA: h wide, w tall
-    { S360_PROF(st, "k_isp_iir_columns", (double)px * 64); k_isp_iir_columns<<<iDivUp(h, 128), 128, 0, st>>>(tA, h, w, alpha, P.maxVal, scratch, tB); }     // horizontal pass
-    { S360_PROF(st, "k_isp_transpose", (double)px * 32); k_isp_transpose<<<dim3(iDivUp(h, 32), iDivUp(w, 32)), tb, 0, st>>>(tB, h, w, tA); }             // tA: w wide, h tall
-    { S360_PROF(st, "k_isp_iir_columns", (double)px * 64); k_isp_iir_columns<<<iDivUp(w, 128), 128, 0, st>>>(tA, w, h, alpha, P.maxVal, scratch, tB); }     // vertical pass
+    { S360_PROF(st, "k_isp_transpose", (double)all * 32); k_isp_transpose<<<dim3(iDivUp(w, 32), iDivUp(h, 32), n), tb, 0, st>>>(rgb, w, h, tA); }           // tA: h wide, w tall
+    { S360_PROF(st, "k_isp_iir_columns", (double)all * 64); k_isp_iir_columns<<<dim3(iDivUp(h, 128), n), 128, 0, st>>>(tA, h, w, alpha, P.maxVal, scratch, tB); }   // horizontal pass
+    { S360_PROF(st, "k_isp_transpose", (double)all * 32); k_isp_transpose<<<dim3(iDivUp(h, 32), iDivUp(w, 32), n), tb, 0, st>>>(tB, h, w, tA); }           // tA: w wide, h tall
+    { S360_PROF(st, "k_isp_iir_columns", (double)all * 64); k_isp_iir_columns<<<dim3(iDivUp(w, 128), n), 128, 0, st>>>(tA, w, h, alpha, P.maxVal, scratch, tB); }   // vertical pass
     lp = tB;
     g_launchCount += 4;
   }
   {
-    S360_PROF(st, "k_isp_finish", (double)px * ((lp ? 32 : 16) + 3 * (outputBpp_ / 8)));
-    const unsigned blocks = (unsigned)((px + 255) / 256);
+    S360_PROF(st, "k_isp_finish", (double)all * ((lp ? 32 : 16) + 3 * (highByte ? 1 : outputBpp_ / 8)));
+    const dim3 blocks((unsigned)((px + 255) / 256), n);
     const float aR = 1.0f + sharpening_.x, aG = 1.0f + sharpening_.y, aB = 1.0f + sharpening_.z;
-    if (highByte) k_isp_finish<unsigned char, true><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned char*>(outDev));
-    else if (outputBpp_ == 8) k_isp_finish<unsigned char, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned char*>(outDev));
-    else k_isp_finish<unsigned short, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, reinterpret_cast<unsigned short*>(outDev));
+    if (highByte) k_isp_finish<unsigned char, true><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, B);
+    else if (outputBpp_ == 8) k_isp_finish<unsigned char, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, B);
+    else k_isp_finish<unsigned short, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, B);
     ++g_launchCount;
   }
   S360_CUDA_CHECK(cudaGetLastError());

@@ -5,10 +5,11 @@
 //   render/ImageWarper.cpp:181-199) -> flattenLayersAlphaSoftmax (util/CvUtil.cpp:336-360) -> * 255/65535.
 // The warp tables are frame-invariant: the host builds them once per (rig, equirect size) with the reference's arithmetic (float
 // sinf/cosf of the C library, the double camera model) and they stay resident, exactly the reference's "precomputed projection".
-// Float path: the blend's expf (and powf when gamma != 1) come from the device's math library, so the result is within a stated
-// tolerance of the CPU's, not bit-identical (tests/test_gpu_preview.py).
+// The blend's expf is the exact port of the host's (expf_bits.cuh): bit-identical to the reference build for gamma == 1 (its default).
+// gamma != 1 goes through the device's powf: stated tolerance (tests/test_gpu_preview.py).
 #include <cmath>
 #include <vector>
+#include "expf_bits.cuh"
 #include "kernels.h"
 #include "rig.h"
 
@@ -89,7 +90,7 @@ k_preview_render(const float4* __restrict__ layers, int lw, int lh, const float2
   for (int i = 0; i < 3; ++i) {
     const float2 m = __ldg(warp + i * plane + px);
     const float4 c = remapCubicF4(layers + (size_t)i * lw * lh, lw, lh, m.x, m.y, tabF);
-    const float alpha = expf(softmaxCoef * c.w) - 1.0f;
+    const float alpha = expfHostBits(softmaxCoef * c.w) - 1.0f;   // exp() on a float inside namespace cv is std::exp(float) = expf
     sb = sb + alpha * c.x; sg = sg + alpha * c.y; sr = sr + alpha * c.z;   // sumColor += alpha * Vec3f(...)
     sumAlpha += alpha;
   }

@@ -131,8 +131,8 @@ def test_raw_to_panorama_on_device(frames17):
     isp.setBitsPerPixel(16); isp.setDemosaicFilter(2); isp.setResize(1); isp.enableToneMap()
     d_raw = [torch.from_numpy(r.view(np.int16)).cuda() for r in raws]
     d_bgr = [torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda") for _ in raws]
-    for r, o in zip(d_raw, d_bgr):
-        isp.frameImageDev(c, r.data_ptr(), w, h, 16, o.data_ptr())
+    isp.frameImageDev(c, d_raw[0].data_ptr(), w, h, 16, d_bgr[0].data_ptr())                                         # one camera alone
+    isp.frameImagesDev(c, [r.data_ptr() for r in d_raw[1:]], w, h, 16, [o.data_ptr() for o in d_bgr[1:]])            # the other 16 in shared launches
     eq_w, eq_h, cw, ch = c.output_size(params)
     d_eq = torch.zeros((eq_h, eq_w, 3), dtype=torch.uint8, device="cuda")
     d_cube = torch.zeros((ch, cw, 3), dtype=torch.uint8, device="cuda")
@@ -162,3 +162,27 @@ def test_reference_build_with_b200_isp_adapter():
         assert np.array_equal(a, b)
     with pytest.raises(RuntimeError, match="frequency"):
         rb.isp_process_b200(CONFIGS["sensor_a"], raw, 1)
+
+
+def test_isp_batch_of_cameras(ctx):
+    """s360_isp_process_frames_dev: the cameras of a frame through shared launches (blockIdx.z = image) == one call per camera."""
+    torch = pytest.importorskip("torch")
+    raws = [synth.bayer_frame(136, 200, np.uint16, seed=40 + k) for k in range(5)]
+    isp = api.CameraIsp(CONFIGS["sensor_a"], 16)
+    isp.setBitsPerPixel(16); isp.setDemosaicFilter(2); isp.setResize(1); isp.enableToneMap()
+    single = [isp.getImage(ctx, r) for r in raws]
+    if torch.cuda.is_available():
+        d_raw = [torch.from_numpy(r.view(np.int16)).cuda() for r in raws]
+        d_out = [torch.zeros((136, 200, 3), dtype=torch.uint8, device="cuda") for _ in raws]
+        isp.frameImagesDev(ctx, [t.data_ptr() for t in d_raw], 200, 136, 16, [t.data_ptr() for t in d_out])
+        ctx.synchronize()
+        outs = [t.cpu().numpy() for t in d_out]
+    else:   # tools/emu: "device" memory is host memory
+        outs = [np.zeros((136, 200, 3), np.uint8) for _ in raws]
+        isp.frameImagesDev(ctx, [r.ctypes.data for r in raws], 200, 136, 16, [o.ctypes.data for o in outs])
+        ctx.synchronize()
+    for o, s in zip(outs, single):
+        assert np.array_equal(o, (s >> 8).astype(np.uint8))
+    with pytest.raises(api.VrCamException, match="batch size"):
+        isp.frameImagesDev(ctx, [0] * 40, 200, 136, 16, [0] * 40)
+    isp.close()

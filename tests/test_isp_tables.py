@@ -103,9 +103,9 @@ int main() {
 def test_expf_port_matches_libm():
     """expfHostBits (the device function the unsharp mask's noise coring uses) is extracted from the CUDA source, compiled for the host
     and compared with the C library's expf on ~35 million float bit patterns: identical bits."""
-    src = open(os.path.join(ROOT, "surround360_b200", "csrc", "isp_kernels.cu")).read()
+    src = open(os.path.join(ROOT, "surround360_b200", "csrc", "expf_bits.cuh")).read()
     a = src.index("static __device__ const unsigned long long kExp2fTab[32]")
-    b = src.index("// ----", src.index("__device__ __forceinline__ float expfHostBits"))
+    b = src.index("}  // namespace s360")
     with tempfile.TemporaryDirectory() as d:
         cpp = os.path.join(d, "t.cpp"); exe = os.path.join(d, "t")
         open(cpp, "w").write(EXPF_TEST % src[a:b].replace("static __device__ const", "static const"))
