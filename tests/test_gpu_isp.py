@@ -186,3 +186,33 @@ def test_isp_batch_of_cameras(ctx):
     with pytest.raises(api.VrCamException, match="batch size"):
         isp.frameImagesDev(ctx, [0] * 40, 200, 136, 16, [0] * 40)
     isp.close()
+
+
+def test_raw2rgb_cli(ctx, tmp_path):
+    """surround360_b200/bin/Raw2Rgb with the reference's flags (Raw2Rgb.cpp:33-45): grey 16-bit PNG and headerless .raw input, 8- and
+    16-bit PNG output; the files hold what the library call returns (and the reference build's result)."""
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    exe = os.path.join(os.path.dirname(HERE), "surround360_b200", "bin", "Raw2Rgb")
+    raw = synth.bayer_frame(136, 200, np.uint16, seed=9)
+    cfg = json.loads(CONFIGS["sensor_a"])
+    cfg["CameraIsp"].update(width=200, height=136)
+    cfg_path = str(tmp_path / "isp.json"); open(cfg_path, "w").write(json.dumps(cfg))
+    png_in = str(tmp_path / "raw.png"); assert cv2.imwrite(png_in, raw)
+    raw_in = str(tmp_path / "frame.raw"); raw.tofile(raw_in)
+    for src, bpp, extra in ((png_in, 16, []), (raw_in, 8, ["--demosaic_filter", "0", "--disable_tone_curve"])):
+        out = str(tmp_path / f"out{bpp}.png")
+        p = subprocess.run([exe, "--input_image_path", src, "--output_image_path", out, "--isp_config_path", cfg_path, "--output_bpp", str(bpp)] + extra,
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-400:]
+        assert "Runtime = " in p.stderr
+        got = cv2.imread(out, cv2.IMREAD_UNCHANGED)
+        want = run_gpu(ctx, "sensor_a", raw, 0 if extra else 2, 1, bpp, not extra)
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+        if rb.available():
+            assert np.array_equal(got, run_ref("sensor_a", raw, 0 if extra else 2, 1, bpp, not extra))
+    p = subprocess.run([exe, "--input_image_path", png_in, "--output_image_path", str(tmp_path / "x.png"), "--isp_config_path", cfg_path, "--demosaic_filter", "1"],
+                       capture_output=True, text=True)
+    assert p.returncode != 0 and "frequency" in p.stderr
+    p = subprocess.run([exe, "--input_image_path", png_in, "--output_image_path", str(tmp_path / "x.png")], capture_output=True, text=True)
+    assert p.returncode != 0 and "isp_config_path" in p.stderr
