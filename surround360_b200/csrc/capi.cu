@@ -488,6 +488,12 @@ int s360_hyper_preview(s360_ctx* c, const uint16_t* rawTop, const uint16_t* rawB
 }
 
 // ---- soft ISP (isp.h) ----
+namespace {
+struct ProfActivate {   // events around the launches made by this thread while s360_profile_enable(ctx, 2) is on
+  explicit ProfActivate(s360_ctx* c) { c->kernelProf.on = c->profileKernels; s360::t_kernelProf = c->profileKernels ? &c->kernelProf : nullptr; }
+  ~ProfActivate() { s360::t_kernelProf = nullptr; }
+};
+}  // namespace
 struct s360_isp { s360::IspPipeline pipe; s360_isp(const char* j, int bpp) : pipe(j, bpp) {} };
 int s360_isp_create(const char* ispJson, int outputBpp, s360_isp** out) {
   S360_API_BEGIN
@@ -517,6 +523,7 @@ int s360_isp_process_dev(s360_ctx* c, s360_isp* isp, const void* rawDev, int inW
   useDevice(c);
   require(isp != nullptr, "null isp");
   require(inW > 0 && inH > 0, "bad image size");
+  ProfActivate prof(c);
   isp->pipe.process(c->stream, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8), outDev, swizzle != 0);
   S360_API_END
 }
@@ -525,6 +532,7 @@ int s360_isp_process_frame_dev(s360_ctx* c, s360_isp* isp, const void* rawDev, i
   useDevice(c);
   require(isp != nullptr, "null isp");
   require(inW > 0 && inH > 0, "bad image size");
+  ProfActivate prof(c);
   isp->pipe.process(c->stream, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8), outBgr8Dev, true, true);
   S360_API_END
 }
@@ -534,6 +542,7 @@ int s360_isp_process_frames_dev(s360_ctx* c, s360_isp* isp, int n, const void* c
   useDevice(c);
   require(isp != nullptr && rawDev && outBgr8Dev, "null argument");
   require(inW > 0 && inH > 0, "bad image size");
+  ProfActivate prof(c);
   isp->pipe.processBatch(c->stream, n, rawDev, inW, inH, depthBits, strideBytes ? strideBytes : (size_t)inW * (depthBits / 8),
                          reinterpret_cast<void* const*>(outBgr8Dev), true, true);
   S360_API_END
