@@ -210,106 +210,23 @@ k_isp_demosaic_edge_aware(const float* __restrict__ greenAll, const float* __res
   rgb[(size_t)i * w + j] = ispColorCorrect(P, lut, r, g, b);
 }
 
-// 32 x 32 tile transpose of 16-byte pixels (the horizontal IIR pass runs along columns of the transposed image)
-__global__ void k_isp_transpose(const float4* __restrict__ srcAll, int w, int h, float4* __restrict__ dstAll) {
-  __shared__ float4 tile[32][33];
-  const float4* __restrict__ src = srcAll + (size_t)blockIdx.z * w * h;
-  float4* __restrict__ dst = dstAll + (size_t)blockIdx.z * w * h;
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int x = bx + threadIdx.x, y = by + r;
-    if (x < w && y < h) tile[r][threadIdx.x] = src[(size_t)y * w + x];
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int y = by + threadIdx.x, x = bx + r;
-    if (x < w && y < h) dst[(size_t)x * h + y] = tile[threadIdx.x][r];
-  }
-}
-
-// One pass of iirLowPass<ReflectBoundary, ReflectBoundary, Vec3f> (Filter.h:38-96) along the columns of a w-wide, n-tall image:
-// causal sweep into `buf`, anticausal sweep out of it, clamped to [0, maxVal]. One thread per column and image (blockIdx.y); the
-// recurrence v = ip * (1 - alpha) + v * alpha is sequential by definition, so the rows are fetched kIspIirBatch at a time and the
-// loads of the NEXT batch are in flight while the dependent lerps of the current one execute (a step would otherwise expose a full
-// memory round trip).
-constexpr int kIspIirBatch = 8;
-__global__ void __launch_bounds__(128)
-k_isp_iir_columns(const float4* __restrict__ inAll, int w, int n, float alpha, float maxVal, float4* __restrict__ bufAll, float4* __restrict__ outAll) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= w) return;
-  const size_t img = (size_t)blockIdx.y * w * n;
-  const float4* __restrict__ in = inAll + img;
-  float4* __restrict__ buf = bufAll + img;
-  float4* __restrict__ out = outAll + img;
-  const float om = 1.0f - alpha;
-  const float4 p0 = in[x];
-  float v0 = p0.x, v1 = p0.y, v2 = p0.z;
-  float4 cur[kIspIirBatch], nxt[kIspIirBatch];
-  // causal: j = 1..n reads row reflect(j), writes buffer row j - 1
-#pragma unroll
-  for (int u = 0; u < kIspIirBatch; ++u)
-    if (1 + u <= n) cur[u] = in[(size_t)ispReflect(1 + u, n) * w + x];
-  for (int j0 = 1; j0 <= n; j0 += kIspIirBatch) {
-#pragma unroll
-    for (int u = 0; u < kIspIirBatch; ++u)
-      if (j0 + kIspIirBatch + u <= n) nxt[u] = in[(size_t)ispReflect(j0 + kIspIirBatch + u, n) * w + x];
-#pragma unroll
-    for (int u = 0; u < kIspIirBatch; ++u)
-      if (j0 + u <= n) {
-        v0 = cur[u].x * om + v0 * alpha;
-        v1 = cur[u].y * om + v1 * alpha;
-        v2 = cur[u].z * om + v2 * alpha;
-        buf[(size_t)(j0 + u - 1) * w + x] = make_float4(v0, v1, v2, 0.0f);
-      }
-#pragma unroll
-    for (int u = 0; u < kIspIirBatch; ++u) cur[u] = nxt[u];
-  }
-  // anticausal: j = n-2..-1 reads buffer row reflect(j), writes row j + 1. The first batch reads rows this thread wrote last.
-#pragma unroll
-  for (int u = 0; u < kIspIirBatch; ++u)
-    if (n - 2 - u >= -1) cur[u] = buf[(size_t)ispReflect(n - 2 - u, n) * w + x];
-  for (int j0 = n - 2; j0 >= -1; j0 -= kIspIirBatch) {
-#pragma unroll
-    for (int u = 0; u < kIspIirBatch; ++u)
-      if (j0 - kIspIirBatch - u >= -1) nxt[u] = buf[(size_t)ispReflect(j0 - kIspIirBatch - u, n) * w + x];
-#pragma unroll
-    for (int u = 0; u < kIspIirBatch; ++u)
-      if (j0 - u >= -1) {
-        v0 = cur[u].x * om + v0 * alpha;
-        v1 = cur[u].y * om + v1 * alpha;
-        v2 = cur[u].z * om + v2 * alpha;
-        out[(size_t)(j0 - u + 1) * w + x] = make_float4(ispClamp(v0, 0.0f, maxVal), ispClamp(v1, 0.0f, maxVal), ispClamp(v2, 0.0f, maxVal), 0.0f);
-      }
-#pragma unroll
-    for (int u = 0; u < kIspIirBatch; ++u) cur[u] = nxt[u];
-  }
-}
-
-// sharpenWithIirLowPass (Filter.h:98-130) when `lp` is given, then getImage's conversion (CameraIsp.h:1275-1299): the float -> 8/16
-// bit stores truncate like the reference's implicit conversions; c0/c1/c2 = 2/1/0 when swizzling to BGR
-// HIGH8: the 16-bit result narrowed the way cv::imread(CV_LOAD_IMAGE_COLOR) narrows the 16-bit PNG the reference's Unpacker writes
-// (high byte; RigDescription.cpp:97-101 reads what Unpacker.cpp:187-190 wrote) -- the bytes the renderer would load
+// sharpenWithIirLowPass for one pixel (Filter.h:98-130) then getImage's conversion (CameraIsp.h:1275-1299): the float -> 8/16 bit
+// stores truncate like the reference's implicit conversions; c0/c2 = 2/0 when swizzling to BGR. HIGH8: the 16-bit result narrowed
+// the way cv::imread(CV_LOAD_IMAGE_COLOR) narrows the 16-bit PNG the reference's Unpacker writes (high byte; RigDescription.cpp:97-101
+// reads what Unpacker.cpp:187-190 wrote) -- the bytes the renderer would load.
+struct IspFinish { float aR, aG, aB, noiseCore, maxVal; int swizzle; };
 template <typename T, bool HIGH8>
-__global__ void __launch_bounds__(256)
-k_isp_finish(const float4* __restrict__ rgb, const float4* __restrict__ lp, size_t n, float aR, float aG, float aB, float noiseCore, float maxVal,
-             int swizzle, IspBatch B) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t g = (size_t)blockIdx.y * n + i;   // pixel i of image blockIdx.y
-  T* __restrict__ out = reinterpret_cast<T*>(B.out[blockIdx.y]);
-  float4 p = rgb[g];
-  if (lp) {
-    const float4 l = lp[g];
-    const float h0 = p.x - l.x, h1 = p.y - l.y, h2 = p.z - l.z;
-    const float n0 = 1.0f - expfHostBits(-(h0 * h0 * noiseCore));
-    const float n1 = 1.0f - expfHostBits(-(h1 * h1 * noiseCore));
-    const float n2 = 1.0f - expfHostBits(-(h2 * h2 * noiseCore));
-    p.x = ispClamp(l.x + h0 * n0 * aR, 0.0f, maxVal);
-    p.y = ispClamp(l.y + h1 * n1 * aG, 0.0f, maxVal);
-    p.z = ispClamp(l.z + h2 * n2 * aB, 0.0f, maxVal);
+__device__ __forceinline__ void ispStorePixel(float4 p, bool sharpen, float l0, float l1, float l2, const IspFinish& F, T* __restrict__ o) {
+  if (sharpen) {
+    const float h0 = p.x - l0, h1 = p.y - l1, h2 = p.z - l2;
+    const float n0 = 1.0f - expfHostBits(-(h0 * h0 * F.noiseCore));
+    const float n1 = 1.0f - expfHostBits(-(h1 * h1 * F.noiseCore));
+    const float n2 = 1.0f - expfHostBits(-(h2 * h2 * F.noiseCore));
+    p.x = ispClamp(l0 + h0 * n0 * F.aR, 0.0f, F.maxVal);
+    p.y = ispClamp(l1 + h1 * n1 * F.aG, 0.0f, F.maxVal);
+    p.z = ispClamp(l2 + h2 * n2 * F.aB, 0.0f, F.maxVal);
   }
-  const int c0 = swizzle ? 2 : 0, c2 = swizzle ? 0 : 2;
-  T* o = out + i * 3;
+  const int c0 = F.swizzle ? 2 : 0, c2 = F.swizzle ? 0 : 2;
   if (HIGH8) {
     o[c0] = (T)((int)p.x >> 8);
     o[1] = (T)((int)p.y >> 8);
@@ -319,6 +236,87 @@ k_isp_finish(const float4* __restrict__ rgb, const float4* __restrict__ lp, size
     o[1] = (T)(int)p.y;
     o[c2] = (T)(int)p.z;
   }
+}
+
+// One pass of iirLowPass<ReflectBoundary, ReflectBoundary, Vec3f> (Filter.h:38-96) over the lines of an image: causal sweep into
+// `buf`, anticausal sweep out of it, clamped to [0, maxVal]. A thread owns one line (a row for the horizontal pass, a column for the
+// vertical one) of one image (blockIdx.y): element p of line l sits at l * lineStride + p * posStride, so the row pass needs no
+// transposed copy -- a thread then reads its own 128-byte line per batch of 8 pixels, and the column pass is coalesced across the
+// warp. The recurrence v = ip * (1 - alpha) + v * alpha is sequential by definition: the pixels are fetched kIspIirBatch at a time
+// and the loads of the NEXT batch are in flight while the dependent lerps of the current one execute.
+// FINISH (vertical pass): the low-pass value is consumed on the spot -- cored unsharp mask, clamp, narrowing, store into the output
+// image -- instead of being written out and read back by another kernel.
+constexpr int kIspIirBatch = 8;
+template <bool FINISH, typename T, bool HIGH8>
+__global__ void __launch_bounds__(128)
+k_isp_iir_lines(const float4* __restrict__ inAll, int lines, int n, size_t lineStride, size_t posStride, size_t imgPixels, float alpha, float maxVal,
+                float4* __restrict__ bufAll, float4* __restrict__ outAll, const float4* __restrict__ rgbAll, IspFinish F, IspBatch B) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= lines) return;
+  const size_t img = (size_t)blockIdx.y * imgPixels, base = (size_t)l * lineStride;
+  const float4* __restrict__ in = inAll + img + base;
+  float4* __restrict__ buf = bufAll + img + base;
+  const float om = 1.0f - alpha;
+  const float4 p0 = in[0];
+  float v0 = p0.x, v1 = p0.y, v2 = p0.z;
+  float4 cur[kIspIirBatch], nxt[kIspIirBatch];
+  // causal: j = 1..n reads position reflect(j), writes buffer position j - 1
+#pragma unroll
+  for (int u = 0; u < kIspIirBatch; ++u)
+    if (1 + u <= n) cur[u] = in[(size_t)ispReflect(1 + u, n) * posStride];
+  for (int j0 = 1; j0 <= n; j0 += kIspIirBatch) {
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 + kIspIirBatch + u <= n) nxt[u] = in[(size_t)ispReflect(j0 + kIspIirBatch + u, n) * posStride];
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 + u <= n) {
+        v0 = cur[u].x * om + v0 * alpha;
+        v1 = cur[u].y * om + v1 * alpha;
+        v2 = cur[u].z * om + v2 * alpha;
+        buf[(size_t)(j0 + u - 1) * posStride] = make_float4(v0, v1, v2, 0.0f);
+      }
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u) cur[u] = nxt[u];
+  }
+  // anticausal: j = n-2..-1 reads buffer position reflect(j), produces position j + 1. The first batch reads what this thread wrote last.
+  float4 rc[kIspIirBatch], rn[kIspIirBatch];   // FINISH: the demosaiced pixels of the positions being produced
+#pragma unroll
+  for (int u = 0; u < kIspIirBatch; ++u)
+    if (n - 2 - u >= -1) {
+      cur[u] = buf[(size_t)ispReflect(n - 2 - u, n) * posStride];
+      if (FINISH) rc[u] = rgbAll[img + base + (size_t)(n - 1 - u) * posStride];
+    }
+  for (int j0 = n - 2; j0 >= -1; j0 -= kIspIirBatch) {
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 - kIspIirBatch - u >= -1) {
+        nxt[u] = buf[(size_t)ispReflect(j0 - kIspIirBatch - u, n) * posStride];
+        if (FINISH) rn[u] = rgbAll[img + base + (size_t)(j0 - kIspIirBatch - u + 1) * posStride];
+      }
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u)
+      if (j0 - u >= -1) {
+        v0 = cur[u].x * om + v0 * alpha;
+        v1 = cur[u].y * om + v1 * alpha;
+        v2 = cur[u].z * om + v2 * alpha;
+        const size_t o = base + (size_t)(j0 - u + 1) * posStride;
+        const float l0 = ispClamp(v0, 0.0f, maxVal), l1 = ispClamp(v1, 0.0f, maxVal), l2 = ispClamp(v2, 0.0f, maxVal);
+        if (FINISH) ispStorePixel<T, HIGH8>(rc[u], true, l0, l1, l2, F, reinterpret_cast<T*>(B.out[blockIdx.y]) + o * 3);
+        else outAll[img + o] = make_float4(l0, l1, l2, 0.0f);
+      }
+#pragma unroll
+    for (int u = 0; u < kIspIirBatch; ++u) { cur[u] = nxt[u]; if (FINISH) rc[u] = rn[u]; }
+  }
+}
+
+// getImage's conversion alone (sharpening disabled: one of the three amounts is zero, CameraIsp.h:1245)
+template <typename T, bool HIGH8>
+__global__ void __launch_bounds__(256)
+k_isp_store(const float4* __restrict__ rgb, size_t n, IspFinish F, IspBatch B) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ispStorePixel<T, HIGH8>(rgb[(size_t)blockIdx.y * n + i], false, 0.f, 0.f, 0.f, F, reinterpret_cast<T*>(B.out[blockIdx.y]) + i * 3);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -503,11 +501,11 @@ IspPipeline::~IspPipeline() {
   if (dWork_) cudaFree(dWork_);
 }
 
-// per pixel and image: rgb, tA, tB float4 (48 B) + scratch float4 (16 B); the demosaic's temporaries (raw, gV, gH, green, diff: 5
-// floats, and one flag byte) live in tA / tB / scratch, which the sharpen stage only needs afterwards. Every array holds the n images
-// of a batch back to back.
+// per pixel and image: rgb, tA and scratch, one float4 each (48 B); the demosaic's temporaries (raw, gV, gH, green in tA; the vote
+// byte and the colour difference in scratch) are dead before the sharpen stage re-uses tA (horizontal low pass) and scratch (the
+// recurrences' buffer). Every array holds the n images of a batch back to back.
 void IspPipeline::ensureDevice(int w, int h, int n) {
-  const size_t px = (size_t)w * h, need = px * 64 * n;
+  const size_t px = (size_t)w * h, need = px * 48 * n;
   if (need > workBytes_) {
     if (dWork_) S360_CUDA_CHECK(cudaFree(dWork_));
     dWork_ = nullptr; workBytes_ = 0;
@@ -580,14 +578,13 @@ void IspPipeline::processBatch(cudaStream_t st, int n, const void* const* rawDev
   const size_t px = (size_t)w * h, all = px * n;
   float4* rgb = reinterpret_cast<float4*>(dWork_);
   float4* tA = rgb + all;
-  float4* tB = tA + all;
-  float4* scratch = tB + all;
-  float* raw = reinterpret_cast<float*>(tA);         // demosaic temporaries, dead before the sharpen stage writes tA / tB / scratch
+  float4* scratch = tA + all;
+  float* raw = reinterpret_cast<float*>(tA);         // demosaic temporaries, dead before the sharpen stage writes tA / scratch
   float* gV = raw + all;
   float* gH = gV + all;
   float* green = gH + all;
-  float* diff = reinterpret_cast<float*>(tB);
-  unsigned char* flag = reinterpret_cast<unsigned char*>(scratch);
+  unsigned char* flag = reinterpret_cast<unsigned char*>(scratch);   // bytes [0, all)
+  float* diff = reinterpret_cast<float*>(scratch) + all;             // bytes [4 all, 8 all)
   const float* vigH = dVig_;
   const float* vigV = dVig_ + (size_t)w * 3;
   const dim3 b(32, 8), g(iDivUp(w, 32), iDivUp(h, 8), n);
@@ -606,24 +603,31 @@ void IspPipeline::processBatch(cudaStream_t st, int n, const void* const* rawDev
     { S360_PROF(st, "k_isp_demosaic_edge_aware", (double)all * (8 + 16)); k_isp_demosaic_edge_aware<<<g, b, 0, st>>>(green, diff, P, dLut_, rgb); }
     g_launchCount += 4;
   }
-  const float4* lp = nullptr;
+  IspFinish Fin;
+  Fin.aR = 1.0f + sharpening_.x; Fin.aG = 1.0f + sharpening_.y; Fin.aB = 1.0f + sharpening_.z;
+  Fin.noiseCore = noiseCore_; Fin.maxVal = P.maxVal; Fin.swizzle = swizzle ? 1 : 0;
+  const int outBytes = highByte ? 1 : outputBpp_ / 8;
   if (sharpening_.x != 0.0 && sharpening_.y != 0.0 && sharpening_.z != 0.0) {   // sharpen(), CameraIsp.h:1244-1259
     const float alpha = powf(sharpeningSupport_, 1.0f / 4.0f);                  // Filter.h:46
-    const dim3 tb(32, 8);
-    { S360_PROF(st, "k_isp_transpose", (double)all * 32); k_isp_transpose<<<dim3(iDivUp(w, 32), iDivUp(h, 32), n), tb, 0, st>>>(rgb, w, h, tA); }           // tA: h wide, w tall
-    { S360_PROF(st, "k_isp_iir_columns", (double)all * 64); k_isp_iir_columns<<<dim3(iDivUp(h, 128), n), 128, 0, st>>>(tA, h, w, alpha, P.maxVal, scratch, tB); }   // horizontal pass
-    { S360_PROF(st, "k_isp_transpose", (double)all * 32); k_isp_transpose<<<dim3(iDivUp(h, 32), iDivUp(w, 32), n), tb, 0, st>>>(tB, h, w, tA); }           // tA: w wide, h tall
-    { S360_PROF(st, "k_isp_iir_columns", (double)all * 64); k_isp_iir_columns<<<dim3(iDivUp(w, 128), n), 128, 0, st>>>(tA, w, h, alpha, P.maxVal, scratch, tB); }   // vertical pass
-    lp = tB;
-    g_launchCount += 4;
-  }
-  {
-    S360_PROF(st, "k_isp_finish", (double)all * ((lp ? 32 : 16) + 3 * (highByte ? 1 : outputBpp_ / 8)));
+    float4* lpH = tA;   // horizontal pass: rgb -> lpH (buffer: scratch); the demosaic's temporaries in tA are dead by now
+    {
+      S360_PROF(st, "k_isp_iir_lines(rows)", (double)all * 64);
+      k_isp_iir_lines<false, unsigned char, false><<<dim3(iDivUp(h, 128), n), 128, 0, st>>>(rgb, h, w, (size_t)w, 1, px, alpha, P.maxVal, scratch, lpH, nullptr, Fin, B);
+    }
+    {   // vertical pass of lpH, fused with the unsharp mask and the output conversion
+      S360_PROF(st, "k_isp_iir_lines(cols+finish)", (double)all * (64 + 3 * outBytes));
+      const dim3 gv(iDivUp(w, 128), n);
+      if (highByte) k_isp_iir_lines<true, unsigned char, true><<<gv, 128, 0, st>>>(lpH, w, h, 1, (size_t)w, px, alpha, P.maxVal, scratch, nullptr, rgb, Fin, B);
+      else if (outputBpp_ == 8) k_isp_iir_lines<true, unsigned char, false><<<gv, 128, 0, st>>>(lpH, w, h, 1, (size_t)w, px, alpha, P.maxVal, scratch, nullptr, rgb, Fin, B);
+      else k_isp_iir_lines<true, unsigned short, false><<<gv, 128, 0, st>>>(lpH, w, h, 1, (size_t)w, px, alpha, P.maxVal, scratch, nullptr, rgb, Fin, B);
+    }
+    g_launchCount += 2;
+  } else {
+    S360_PROF(st, "k_isp_store", (double)all * (16 + 3 * outBytes));
     const dim3 blocks((unsigned)((px + 255) / 256), n);
-    const float aR = 1.0f + sharpening_.x, aG = 1.0f + sharpening_.y, aB = 1.0f + sharpening_.z;
-    if (highByte) k_isp_finish<unsigned char, true><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, B);
-    else if (outputBpp_ == 8) k_isp_finish<unsigned char, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, B);
-    else k_isp_finish<unsigned short, false><<<blocks, 256, 0, st>>>(rgb, lp, px, aR, aG, aB, noiseCore_, P.maxVal, swizzle ? 1 : 0, B);
+    if (highByte) k_isp_store<unsigned char, true><<<blocks, 256, 0, st>>>(rgb, px, Fin, B);
+    else if (outputBpp_ == 8) k_isp_store<unsigned char, false><<<blocks, 256, 0, st>>>(rgb, px, Fin, B);
+    else k_isp_store<unsigned short, false><<<blocks, 256, 0, st>>>(rgb, px, Fin, B);
     ++g_launchCount;
   }
   S360_CUDA_CHECK(cudaGetLastError());
