@@ -264,6 +264,37 @@ int s360_isp_process_frame_dev(s360_ctx* ctx, s360_isp* isp, const void* raw_dev
 int s360_isp_process_frames_dev(s360_ctx* ctx, s360_isp* isp, int n, const void* const* raw_dev, int in_w, int in_h, int depth_bits,
                                 size_t stride_bytes, uint8_t* const* out_bgr8_dev);
 
+/* ---- footage container and raw-sample conversion: the Unpacker's front end ----
+ * s360_footage mirrors BinaryFootageFile (source/camera_isp/BinaryFootageFile.h:16-62): the capture software's ".bin" file, a 32-byte
+ * header and, from offset 4096, frame f of camera c at (number_of_cameras * f + c) * frame_bytes. Host I/O (read-only mapping). */
+typedef struct s360_footage s360_footage;
+typedef struct {   /* BinaryFootageFile::MetadataHeader, BinaryFootageFile.h:18-27 */
+  uint32_t magic, timestamp, file_index, file_count, width, height, bits_per_pixel, number_of_cameras;
+} s360_footage_header;
+int s360_footage_open(const char* path, s360_footage** out);                        /* BinaryFootageFile(path) + open(), .cpp:30-101 */
+void s360_footage_close(s360_footage* f);
+/* getMetadata / getNumberOfFrames (.cpp:160-168) / getFrameSize (.cpp:170-172); any output may be NULL */
+int s360_footage_info(s360_footage* f, s360_footage_header* header, uint64_t* frames, uint64_t* frame_bytes);
+/* getFrame (.cpp:143-154): pointer into the mapping, valid until s360_footage_close; error when the camera or frame is outside the file */
+int s360_footage_frame(s360_footage* f, uint32_t frame, uint32_t camera, const uint8_t** data);
+
+/* RawConverter::convert8Frame / convert12Frame (source/camera_isp/RawConverter.cpp:14-59): packed footage samples (bits 8 or 12, dense:
+ * w * h * bits / 8 bytes) -> w x h uint16 (8-bit: v * 0x101; 12-bit: unswizzled and replicated to 16 bits). Host buffers. */
+int s360_raw_convert(s360_ctx* ctx, const void* packed, int bits, int w, int h, uint16_t* out);
+/* n frames of one size, device buffers (pointer arrays on the HOST), asynchronous on the context's stream */
+int s360_raw_convert_dev(s360_ctx* ctx, int n, const void* const* packed_dev, int bits, int w, int h, uint16_t* const* out_dev);
+/* Unpacker.cpp:141-190 for the n cameras of a frame: packed footage samples straight into the ISP (widened inside its first kernel exactly
+ * as RawConverter widens them, then loadImage's 16-bit branch). isp: created with 16 output bits (Unpacker's kOutputBpp). high_byte 0:
+ * out_dev[k] = h x w x 3 uint16 BGR, the image Unpacker writes as PNG; high_byte 1: h x w x 3 uint8, the renderer's input (see
+ * s360_isp_process_frame_dev). Device buffers, pointer arrays on the HOST, asynchronous on the context's stream. */
+int s360_isp_process_footage_dev(s360_ctx* ctx, s360_isp* isp, int n, const void* const* packed_dev, int bits, int w, int h, void* const* out_dev,
+                                 int high_byte);
+
+/* One frame through host buffers (what the Unpacker tool calls per camera and frame): packed: w * h * bits / 8 bytes; out16: h x w x 3
+ * uint16 BGR; raw16_out (may be NULL): the widened samples, w x h uint16 (the --output_raw_dir dump). isp may be NULL when only the raw
+ * dump is wanted (a camera without an ISP configuration, Unpacker.cpp:165-168); then out16 is not written. */
+int s360_isp_process_footage(s360_ctx* ctx, s360_isp* isp, const void* packed, int bits, int w, int h, uint16_t* out16, uint16_t* raw16_out);
+
 /* ---- whole frame ---- */
 
 /* renderStereoPanorama (TRSP:716-972) without file I/O. images: one BGR8 image per rig

@@ -6,6 +6,7 @@
 #   oracle/_ref/TestRenderStereoPanorama   the reference's frame renderer (its own main(), flags, threading, file I/O)
 #   oracle/_ref/libref.so                  the reference's operators behind a small C API (oracle/ref_capi.cpp)
 #   oracle/_ref/libref_preview.so, libref_isp.so   TestHyperPreview and the soft ISP (camera_isp/CameraIsp.h) behind C APIs
+#   oracle/_ref/libref_unpack.so           the footage container reader and raw-sample converter of the Unpacker (BinaryFootageFile, RawConverter)
 # Flags follow the reference's build (surround360_render/CMakeLists.txt: -O3 -std=c++11 -mavx, no -mfma, threads).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -66,4 +67,12 @@ if [ -f "$REPO/surround360_b200/libs360b200.so" ]; then   # the same library wit
   $CXX $CXXFLAGS $INC -I$REF/camera_isp -I$REPO/integration/reference_tree/camera_isp -I$REPO/include -DREF_WITH_B200_ISP -c "$HERE/ref_isp_capi.cpp" -o "$OUT/obj/ref_isp_capi_b200.o"
   $CXX -pthread -shared -o "$OUT/libref_isp_b200.so" "$OUT/obj/ref_isp_capi_b200.o" "$OUT/obj/util_JsonUtil.o" "$OUT/obj/supereasyjson.o" $OBJS -lz -L"$REPO/surround360_b200" -ls360b200 -Wl,-rpath,'$ORIGIN/../../surround360_b200'
 fi
+# the Unpacker's front end: the .bin footage container and the 8 / 12-bit sample converter. The two headers use uint32_t /
+# CHAR_BIT without including <cstdint> / <climits> (older libstdc++ pulled them in through <string>): pre-included on the command line.
+UNP="-include cstdint -include climits -I$REF/camera_isp"
+$CXX $CXXFLAGS $INC $UNP -c "$HERE/ref_unpack_capi.cpp" -o "$OUT/obj/ref_unpack_capi.o" &
+$CXX $CXXFLAGS $INC $UNP -c "$REF/camera_isp/BinaryFootageFile.cpp" -o "$OUT/obj/camera_isp_BinaryFootageFile.o" &
+$CXX $CXXFLAGS $INC $UNP -c "$REF/camera_isp/RawConverter.cpp" -o "$OUT/obj/camera_isp_RawConverter.o" &
+wait
+$CXX -pthread -shared -o "$OUT/libref_unpack.so" "$OUT/obj/ref_unpack_capi.o" "$OUT/obj/camera_isp_BinaryFootageFile.o" "$OUT/obj/camera_isp_RawConverter.o"
 echo "ref_build: built $OUT/TestRenderStereoPanorama and $OUT/libref.so"

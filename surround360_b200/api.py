@@ -451,6 +451,93 @@ class CameraIsp:
         _check(lib().s360_isp_process_dev(ctx.h, self.h, C.c_void_p(raw_dev_ptr), w, h, depth_bits, C.c_size_t(stride_bytes), C.c_void_p(out_dev_ptr), int(swizzle)))
 
 
+    def footageImage(self, ctx, packed, bits, w, h, want_raw=False):
+        """Unpacker.cpp:141-190 for one camera frame: packed footage samples (bytes as they lie in the .bin) -> (h, w, 3) uint16 BGR, the
+        image the Unpacker writes as PNG; with want_raw also the widened (h, w) uint16 samples. The ISP must have 16 output bits."""
+        packed = np.ascontiguousarray(packed, np.uint8).reshape(-1)
+        if packed.size != w * h * bits // 8:
+            raise VrCamException("packed frame size does not match w * h * bits / 8")
+        out = np.zeros((h, w, 3), np.uint16)
+        raw = np.zeros((h, w), np.uint16) if want_raw else None
+        _check(lib().s360_isp_process_footage(ctx.h, self.h, _p(packed), bits, w, h, _p(out), _p(raw) if want_raw else None))
+        return (out, raw) if want_raw else out
+
+    def footageImagesDev(self, ctx, packed_dev_ptrs, bits, w, h, out_dev_ptrs, high_byte=False):
+        """The cameras of one frame in shared launches, device pointers (s360_isp_process_footage_dev)."""
+        n = len(packed_dev_ptrs)
+        a = (C.c_void_p * n)(*[int(p) for p in packed_dev_ptrs]); b = (C.c_void_p * n)(*[int(p) for p in out_dev_ptrs])
+        _check(lib().s360_isp_process_footage_dev(ctx.h, self.h, n, a, bits, w, h, b, int(high_byte)))
+
+
+class RawConverter:
+    """camera_isp/RawConverter.h:19-30 on the GPU: packed footage samples -> (h, w) uint16."""
+
+    @staticmethod
+    def _convert(ctx, raw_frame, bits, width, height):
+        packed = np.ascontiguousarray(raw_frame, np.uint8).reshape(-1)
+        if packed.size < width * height * bits // 8:
+            raise VrCamException("packed frame smaller than width * height * bits / 8")
+        out = np.zeros((height, width), np.uint16)
+        _check(lib().s360_raw_convert(ctx.h, _p(packed), bits, width, height, _p(out)))
+        return out
+
+    @staticmethod
+    def convert8Frame(ctx, raw_frame, width, height):
+        return RawConverter._convert(ctx, raw_frame, 8, width, height)
+
+    @staticmethod
+    def convert12Frame(ctx, raw_frame, width, height):
+        return RawConverter._convert(ctx, raw_frame, 12, width, height)
+
+
+class FootageHeader(C.Structure):   # BinaryFootageFile::MetadataHeader, BinaryFootageFile.h:18-27
+    _fields_ = [(n, C.c_uint32) for n in ("magic", "timestamp", "fileIndex", "fileCount", "width", "height", "bitsPerPixel", "numberOfCameras")]
+
+
+class BinaryFootageFile:
+    """camera_isp/BinaryFootageFile.h:16-62 (host I/O; no device needed): the capture software's .bin container."""
+
+    def __init__(self, file_path):
+        self.h = C.c_void_p()
+        _check(lib().s360_footage_open(str(file_path).encode(), C.byref(self.h)))
+        self._hd = FootageHeader()
+        frames, fbytes = C.c_uint64(), C.c_uint64()
+        _check(lib().s360_footage_info(self.h, C.byref(self._hd), C.byref(frames), C.byref(fbytes)))
+        self._frames, self._frame_bytes = frames.value, fbytes.value
+
+    def close(self):
+        if self.h:
+            lib().s360_footage_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def getMetadata(self):
+        return self._hd
+
+    def getNumberOfCameras(self):
+        return self._hd.numberOfCameras
+
+    def getNumberOfFrames(self):
+        return self._frames
+
+    def getFrameSize(self):
+        return self._frame_bytes
+
+    def getBitsPerPixel(self):
+        return self._hd.bitsPerPixel
+
+    def getFrame(self, frame_number, camera_number):
+        """The frame's packed bytes (a copy of the mapped range)."""
+        ptr = C.POINTER(C.c_uint8)()
+        _check(lib().s360_footage_frame(self.h, frame_number, camera_number, C.byref(ptr)))
+        return np.ctypeslib.as_array(ptr, shape=(self._frame_bytes,)).copy()
+
+
 def saveFlowToFile(flow, path):  # CvUtil.cpp:159-182
     f = _c(flow, np.float32)
     _check(lib().s360_flow_save(path.encode(), _p(f), f.shape[1], f.shape[0]))

@@ -6,6 +6,7 @@
 #include <sstream>
 #include "pipeline.h"
 #include "isp.h"
+#include "footage.h"
 
 using namespace s360;
 
@@ -562,6 +563,89 @@ int s360_isp_process(s360_ctx* c, s360_isp* isp, const void* raw, int inW, int i
   S360_CUDA_CHECK(cudaMemcpy2DAsync(dRaw.p, rowBytes, raw, strideBytes, rowBytes, inH, cudaMemcpyHostToDevice, st));
   isp->pipe.process(st, dRaw.p, inW, inH, depthBits, rowBytes, dOut.p, swizzle != 0);
   S360_CUDA_CHECK(cudaMemcpyAsync(out, dOut.p, outBytes, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
+// ---- footage container + raw-sample conversion (footage.h, isp.h) ----
+struct s360_footage { s360::FootageFile file; explicit s360_footage(const char* p) : file(p) {} };
+int s360_footage_open(const char* path, s360_footage** out) {
+  S360_API_BEGIN
+  require(path && out, "null argument");
+  *out = new s360_footage(path);
+  S360_API_END
+}
+void s360_footage_close(s360_footage* f) { delete f; }
+int s360_footage_info(s360_footage* f, s360_footage_header* header, uint64_t* frames, uint64_t* frameBytes) {
+  S360_API_BEGIN
+  require(f != nullptr, "null footage file");
+  static_assert(sizeof(s360_footage_header) == sizeof(s360::FootageHeader), "header layout");
+  if (header) std::memcpy(header, &f->file.header(), sizeof *header);
+  if (frames) *frames = f->file.numberOfFrames();
+  if (frameBytes) *frameBytes = f->file.frameSize();
+  S360_API_END
+}
+int s360_footage_frame(s360_footage* f, uint32_t frame, uint32_t camera, const uint8_t** data) {
+  S360_API_BEGIN
+  require(f != nullptr && data != nullptr, "null argument");
+  *data = f->file.frame(frame, camera);
+  S360_API_END
+}
+int s360_raw_convert_dev(s360_ctx* c, int n, const void* const* packedDev, int bits, int w, int h, uint16_t* const* outDev) {
+  S360_API_BEGIN
+  useDevice(c);
+  ProfActivate prof(c);
+  s360::rawConvertBatch(c->stream, n, packedDev, bits, w, h, reinterpret_cast<void* const*>(outDev));
+  S360_API_END
+}
+int s360_raw_convert(s360_ctx* c, const void* packed, int bits, int w, int h, uint16_t* out) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(packed && out, "null argument");
+  require((bits == 8 || bits == 12) && w > 0 && h > 0, "footage samples are 8 or 12 bits per pixel");
+  const size_t inBytes = (size_t)w * h * bits / 8, outBytes = (size_t)w * h * 2;
+  DeviceBuffer dIn(inBytes), dOut(outBytes);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dIn.p, packed, inBytes, cudaMemcpyHostToDevice, c->stream));
+  const void* src = dIn.p; void* dst = dOut.p;
+  s360::rawConvertBatch(c->stream, 1, &src, bits, w, h, &dst);
+  S360_CUDA_CHECK(cudaMemcpyAsync(out, dOut.p, outBytes, cudaMemcpyDeviceToHost, c->stream));
+  S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  S360_API_END
+}
+int s360_isp_process_footage_dev(s360_ctx* c, s360_isp* isp, int n, const void* const* packedDev, int bits, int w, int h, void* const* outDev, int highByte) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(isp != nullptr && packedDev && outDev, "null argument");
+  require(w > 0 && h > 0, "bad image size");
+  require(bits == 8 || bits == 12, "footage samples are 8 or 12 bits per pixel");
+  ProfActivate prof(c);
+  isp->pipe.processBatch(c->stream, n, packedDev, w, h, 16, (size_t)w * bits / 8, outDev, true, highByte != 0, bits);
+  S360_API_END
+}
+
+int s360_isp_process_footage(s360_ctx* c, s360_isp* isp, const void* packed, int bits, int w, int h, uint16_t* out16, uint16_t* raw16Out) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(packed != nullptr, "null argument");
+  require(isp == nullptr || out16 != nullptr, "null output image");
+  require(w > 0 && h > 0, "bad image size");
+  require(bits == 8 || bits == 12, "footage samples are 8 or 12 bits per pixel");
+  require(isp == nullptr || isp->pipe.outputBpp() == 16, "the Unpacker's ISP has 16 output bits");
+  const size_t px = (size_t)w * h, inBytes = px * bits / 8;
+  cudaStream_t st = c->stream;
+  DeviceBuffer dIn(inBytes), dRaw(raw16Out ? px * 2 : 0), dOut(isp ? px * 6 : 0);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dIn.p, packed, inBytes, cudaMemcpyHostToDevice, st));
+  const void* src = dIn.p;
+  if (raw16Out) {
+    void* dst = dRaw.p;
+    s360::rawConvertBatch(st, 1, &src, bits, w, h, &dst);
+    S360_CUDA_CHECK(cudaMemcpyAsync(raw16Out, dRaw.p, px * 2, cudaMemcpyDeviceToHost, st));
+  }
+  if (isp) {
+    void* dst = dOut.p;
+    isp->pipe.processBatch(st, 1, &src, w, h, 16, (size_t)w * bits / 8, &dst, true, false, bits);
+    S360_CUDA_CHECK(cudaMemcpyAsync(out16, dOut.p, px * 6, cudaMemcpyDeviceToHost, st));
+  }
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
   S360_API_END
 }

@@ -48,8 +48,11 @@ class IspPipeline {
   void process(cudaStream_t st, const void* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* outDev, bool swizzle, bool highByte = false);
   // n images of one size through the same launches (blockIdx.z / .y = image): the rig's 17 cameras per frame. The IIR passes have
   // only one thread per image line, so batching is what fills the GPU there.
+  // footageBits 8 / 12 (with depthBits 16): rawDev holds the footage container's packed samples (row pitch strideBytes = inW *
+  // footageBits / 8 when dense); they are widened on the fly as the Unpacker's RawConverter widens them before loadImage
+  // (Unpacker.cpp:141-180, RawConverter.cpp:14-59).
   void processBatch(cudaStream_t st, int n, const void* const* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* const* outDev, bool swizzle,
-                    bool highByte = false);
+                    bool highByte = false, int footageBits = 0);
 
  private:
   void setup();               // :612-715
@@ -77,6 +80,10 @@ class IspPipeline {
   void* dWork_ = nullptr;
   size_t workBytes_ = 0;
 };
+
+// RawConverter::convert8Frame / convert12Frame (camera_isp/RawConverter.cpp:14-59) for n frames of one size: packed footage samples
+// (bits 8 or 12, dense) -> w x h uint16 planes. Device pointers in host arrays, asynchronous on `st`.
+void rawConvertBatch(cudaStream_t st, int n, const void* const* srcDev, int bits, int w, int h, void* const* dstDev);
 
 // host restatement of the vignette curve evaluation (BezierCurve, MathUtil.h:186-216; curveHAtPixel / curveVAtPixel, CameraIsp.h:707-713)
 void ispBezier(const std::vector<IspP3>& pts, float t, float out[3]);

@@ -25,14 +25,29 @@ __device__ __forceinline__ int ispReflect(int x, int r) { return x < 0 ? -x : x 
 __device__ __forceinline__ float ispClamp(float x, float a, float b) { return x < a ? a : x > b ? b : x; }    // MathUtil.h:36-39
 __device__ __forceinline__ int ispChan(const IspDev& P, int i, int j) { return P.chan[(i & 1) * 2 + (j & 1)]; }
 
+// How k_isp_prep reads one raw sample (row pointer, column): plain 8 / 16-bit planes (what loadImage receives, CameraIsp.h:831-857),
+// or the footage container's packed samples widened to 16 bits on the fly exactly as the Unpacker's RawConverter widens them before
+// loadImage (RawConverter.cpp:14-59): 8-bit x 0x101; 12-bit pairs in three bytes b0 b1 b2 -> (b0 << 4 | b1 & 15), (b2 << 4 | b1 >> 4),
+// each replicated to 16 bits (u << 4 | u >> 8). The values are exact integers, so the fused read equals convert + 16-bit load.
+struct RawPlain8 { static __device__ __forceinline__ float at(const unsigned char* row, int x) { return float(row[x]); } };
+struct RawPlain16 { static __device__ __forceinline__ float at(const unsigned char* row, int x) { return float(reinterpret_cast<const unsigned short*>(row)[x]); } };
+__device__ __forceinline__ unsigned footage12Sample(const unsigned char* row, int x) {
+  const unsigned char* p = row + (x >> 1) * 3;
+  const unsigned b1 = p[1];
+  const unsigned u = (x & 1) ? ((unsigned)p[2] << 4 | b1 >> 4) : ((unsigned)p[0] << 4 | (b1 & 0xFu));
+  return (u << 4 | u >> 8) & 0xFFFFu;
+}
+struct RawFootage8 { static __device__ __forceinline__ float at(const unsigned char* row, int x) { return float((unsigned)row[x] * 0x101u); } };
+struct RawFootage12 { static __device__ __forceinline__ float at(const unsigned char* row, int x) { return float(footage12Sample(row, x)); } };
+
 // loadImage/resizeInput (CameraIsp.h:338-358) + blackLevelAdjust (:1106-1126) + antiVignette (:1145-1154) + whiteBalance (:1005-1021)
 // + clampAndStretch (:1128-1143): raw samples -> the float Bayer plane the demosaic reads
-template <typename T>
+template <typename A>
 __global__ void __launch_bounds__(256)
 k_isp_prep(IspBatch B, IspDev P, const float* __restrict__ vigH, const float* __restrict__ vigV, float* __restrict__ rawAll) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= P.w || i >= P.h) return;
-  const T* __restrict__ in = reinterpret_cast<const T*>(B.raw[blockIdx.z]);
+  const unsigned char* __restrict__ in = reinterpret_cast<const unsigned char*>(B.raw[blockIdx.z]);
   const size_t strideBytes = B.strideBytes;
   float* __restrict__ raw = rawAll + (size_t)blockIdx.z * P.w * P.h;
   const int r = P.resize > 1 ? 2 : 1;
@@ -40,11 +55,11 @@ k_isp_prep(IspBatch B, IspDev P, const float* __restrict__ vigH, const float* __
   for (int k = 0; k < P.resize; ++k) {
     const int ip = i * P.resize + k * 2;
     const int ipp = ispReflect(ip + (i % r), P.inH);
-    const T* row = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(in) + (size_t)ipp * strideBytes);
+    const unsigned char* row = in + (size_t)ipp * strideBytes;
     for (int l = 0; l < P.resize; ++l) {
       const int jp = j * P.resize + l * 2;
       const int jpp = ispReflect(jp + (j % r), P.inW);
-      sum += float(row[jpp]);
+      sum += A::at(row, jpp);
     }
   }
   float v = sum * P.areaRecip;
@@ -319,6 +334,81 @@ k_isp_store(const float4* __restrict__ rgb, size_t n, IspFinish F, IspBatch B) {
   ispStorePixel<T, HIGH8>(rgb[(size_t)blockIdx.y * n + i], false, 0.f, 0.f, 0.f, F, reinterpret_cast<T*>(B.out[blockIdx.y]) + i * 3);
 }
 
+// RawConverter::convert12Frame (RawConverter.cpp:34-59) as a stand-alone pass (the Unpacker's --output_raw_dir dump; the ISP reads
+// packed samples directly, RawFootage12). The frame is dense (three bytes per pixel pair, no row padding), so for widths that are a
+// multiple of 8 it is a linear stream: a thread turns 12 bytes (three aligned 32-bit loads) into eight 16-bit samples (one 16-byte
+// store): 3.5 B per pixel of compulsory traffic, all of it coalesced. blockIdx.y = image.
+struct RawBatch { const void* src[kIspMaxBatch]; void* dst[kIspMaxBatch]; };
+__device__ __forceinline__ unsigned rep12(unsigned u) { return (u << 4 | u >> 8) & 0xFFFFu; }
+__global__ void __launch_bounds__(256)
+k_raw_convert12_x8(RawBatch B, size_t groups) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const unsigned* __restrict__ in = reinterpret_cast<const unsigned*>(B.src[blockIdx.y]) + g * 3;
+  const unsigned w0 = __ldg(in), w1 = __ldg(in + 1), w2 = __ldg(in + 2);
+  // bytes b0..b11 little endian in w0 w1 w2; pair k uses bytes 3k, 3k+1, 3k+2
+  auto byteAt = [&](int i) -> unsigned { const unsigned w = i < 4 ? w0 : i < 8 ? w1 : w2; return (w >> (8 * (i & 3))) & 0xFFu; };
+  unsigned px[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned b0 = byteAt(3 * k), b1 = byteAt(3 * k + 1), b2 = byteAt(3 * k + 2);
+    px[2 * k] = rep12(b0 << 4 | (b1 & 0xFu));
+    px[2 * k + 1] = rep12(b2 << 4 | b1 >> 4);
+  }
+  uint4 o;
+  o.x = px[0] | px[1] << 16; o.y = px[2] | px[3] << 16; o.z = px[4] | px[5] << 16; o.w = px[6] | px[7] << 16;
+  reinterpret_cast<uint4*>(B.dst[blockIdx.y])[g] = o;
+}
+// any even width (or unaligned frames): one thread per pixel pair, byte loads
+__global__ void __launch_bounds__(256)
+k_raw_convert12_pairs(RawBatch B, size_t pairs) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= pairs) return;
+  const unsigned char* __restrict__ p = reinterpret_cast<const unsigned char*>(B.src[blockIdx.y]) + g * 3;
+  const unsigned b0 = p[0], b1 = p[1], b2 = p[2];
+  unsigned short* o = reinterpret_cast<unsigned short*>(B.dst[blockIdx.y]) + g * 2;
+  o[0] = (unsigned short)rep12(b0 << 4 | (b1 & 0xFu));
+  o[1] = (unsigned short)rep12(b2 << 4 | b1 >> 4);
+}
+// RawConverter::convert8Frame (RawConverter.cpp:14-32): value * 0x101; four samples per thread
+__global__ void __launch_bounds__(256)
+k_raw_convert8(RawBatch B, size_t n) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned char* __restrict__ in = reinterpret_cast<const unsigned char*>(B.src[blockIdx.y]);
+  unsigned short* out = reinterpret_cast<unsigned short*>(B.dst[blockIdx.y]);
+  for (size_t i = g * 4; i < n && i < g * 4 + 4; ++i) out[i] = (unsigned short)(in[i] * 0x101u);
+}
+
+void rawConvertBatch(cudaStream_t st, int n, const void* const* srcDev, int bits, int w, int h, void* const* dstDev) {
+  if (n < 1 || n > kIspMaxBatch) throw std::runtime_error("raw batch size out of range (1.." + std::to_string(kIspMaxBatch) + ")");
+  if (bits != 8 && bits != 12) throw std::runtime_error("footage samples are 8 or 12 bits per pixel");
+  if (w < 1 || h < 1) throw std::runtime_error("bad image size");
+  // odd widths: the reference's running byte index makes rows straddle bytes and its last pixel reads one byte past the frame
+  if (bits == 12 && (w & 1)) throw std::runtime_error("12-bit footage needs an even width");
+  if (!srcDev || !dstDev) throw std::runtime_error("null image");
+  RawBatch B;
+  std::memset(&B, 0, sizeof B);
+  bool aligned = true;
+  for (int k = 0; k < n; ++k) {
+    if (!srcDev[k] || !dstDev[k]) throw std::runtime_error("null image");
+    B.src[k] = srcDev[k]; B.dst[k] = dstDev[k];
+    aligned = aligned && ((uintptr_t)srcDev[k] & 3) == 0 && ((uintptr_t)dstDev[k] & 15) == 0;
+  }
+  const size_t px = (size_t)w * h;
+  if (bits == 8) {
+    S360_PROF(st, "k_raw_convert8", (double)px * n * 3);
+    k_raw_convert8<<<dim3((unsigned)((px / 4 + 256) / 256), n), 256, 0, st>>>(B, px);
+  } else if ((px & 7) == 0 && aligned) {
+    S360_PROF(st, "k_raw_convert12", (double)px * n * 3.5);
+    k_raw_convert12_x8<<<dim3((unsigned)((px / 8 + 255) / 256), n), 256, 0, st>>>(B, px / 8);
+  } else {
+    S360_PROF(st, "k_raw_convert12", (double)px * n * 3.5);
+    k_raw_convert12_pairs<<<dim3((unsigned)((px / 2 + 255) / 256), n), 256, 0, st>>>(B, px / 2);
+  }
+  ++g_launchCount;
+  S360_CUDA_CHECK(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------------------------------------
 // host: configuration, tables (CameraIsp.h:390-715)
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -526,10 +616,15 @@ void IspPipeline::process(cudaStream_t st, const void* rawDev, int inW, int inH,
 }
 
 void IspPipeline::processBatch(cudaStream_t st, int n, const void* const* rawDev, int inW, int inH, int depthBits, size_t strideBytes, void* const* outDev,
-                               bool swizzle, bool highByte) {
+                               bool swizzle, bool highByte, int footageBits) {
   if (n < 1 || n > kIspMaxBatch) throw std::runtime_error("ISP batch size out of range (1.." + std::to_string(kIspMaxBatch) + ")");
   if (highByte && outputBpp_ != 16) throw std::runtime_error("the high-byte output needs an ISP created with 16 output bits");
   if (depthBits != 8 && depthBits != 16) throw std::runtime_error("input is larger that 16 bits per pixel");   // the reference's message, CameraIsp.h:855
+  if (footageBits) {   // packed container samples, seen by loadImage as the 16-bit plane RawConverter makes of them (Unpacker.cpp:141-180)
+    if (footageBits != 8 && footageBits != 12) throw std::runtime_error("footage samples are 8 or 12 bits per pixel");
+    if (footageBits == 12 && (inW & 1)) throw std::runtime_error("12-bit footage needs an even width");
+    if (depthBits != 16) throw std::runtime_error("footage samples are loaded as 16-bit input");
+  }
   if (!rawDev || !outDev) throw std::runtime_error("null image");
   for (int k = 0; k < n; ++k) if (!rawDev[k] || !outDev[k]) throw std::runtime_error("null image");
   if (demosaicFilter_ == 1) throw std::runtime_error("the frequency-domain demosaic filter (cv::dct) is not implemented: use 0 (bilinear) or 2 (edge aware)");
@@ -539,7 +634,7 @@ void IspPipeline::processBatch(cudaStream_t st, int n, const void* const* rawDev
   //  removeStuckPixels changes nothing, CameraIsp.h:1090-1097)
   const int w = inW / resize_, h = inH / resize_;   // loadImage, CameraIsp.h:832-833
   if (w < 8 || h < 8) throw std::runtime_error("image too small for the ISP (8 x 8 after the resize at least)");
-  if (strideBytes < (size_t)inW * (depthBits / 8)) throw std::runtime_error("row stride smaller than a row");
+  if (strideBytes < (footageBits ? (size_t)inW * footageBits / 8 : (size_t)inW * (depthBits / 8))) throw std::runtime_error("row stride smaller than a row");
   // loadImage: the input depth overrides bitsPerPixel; only the 16-bit case recomputes maxPixelValue (CameraIsp.h:843-853)
   if (depthBits == 8) bitsPerPixel_ = 8;
   else { bitsPerPixel_ = 16; maxPixelValue_ = (1 << bitsPerPixel_) - 1; }
@@ -589,9 +684,11 @@ void IspPipeline::processBatch(cudaStream_t st, int n, const void* const* rawDev
   const float* vigV = dVig_ + (size_t)w * 3;
   const dim3 b(32, 8), g(iDivUp(w, 32), iDivUp(h, 8), n);
   {
-    S360_PROF(st, "k_isp_prep", (double)all * (depthBits / 8) * resize_ * resize_ + (double)all * 4);
-    if (depthBits == 8) k_isp_prep<unsigned char><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
-    else k_isp_prep<unsigned short><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
+    S360_PROF(st, "k_isp_prep", (double)all * (footageBits ? footageBits / 8.0 : depthBits / 8) * resize_ * resize_ + (double)all * 4);
+    if (footageBits == 12) k_isp_prep<RawFootage12><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
+    else if (footageBits == 8) k_isp_prep<RawFootage8><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
+    else if (depthBits == 8) k_isp_prep<RawPlain8><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
+    else k_isp_prep<RawPlain16><<<g, b, 0, st>>>(B, P, vigH, vigV, raw);
   }
   if (demosaicFilter_ == 0) {
     S360_PROF(st, "k_isp_demosaic_bilinear", (double)all * (4 + 16));

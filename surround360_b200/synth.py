@@ -170,3 +170,39 @@ def bayer_frame(h, w, dtype=np.uint16, seed=0):
     flat[rng.integers(0, flat.size, max(flat.size // 4000, 3))] = 1.0                 # hot pixels
     full = 65535.0 if dtype == np.uint16 else 255.0
     return np.clip(0.02 * full + mosaic * 0.9 * full, 0, full).astype(dtype)
+
+
+def pack12(samples):
+    """(h, w) 12-bit sample values (w even) -> the capture software's packed bytes, three per pixel pair: b0 = even >> 4,
+    b1 = (even & 15) | (odd & 15) << 4, b2 = odd >> 4 -- the layout RawConverter::convert12Frame undoes (RawConverter.cpp:34-59)."""
+    s = np.asarray(samples).astype(np.uint16)
+    assert s.ndim == 2 and s.shape[1] % 2 == 0 and int(s.max(initial=0)) < 4096
+    e, o = s[:, 0::2], s[:, 1::2]
+    out = np.empty((s.shape[0], s.shape[1] // 2, 3), np.uint8)
+    out[..., 0] = e >> 4
+    out[..., 1] = (e & 15) | ((o & 15) << 4)
+    out[..., 2] = o >> 4
+    return out.reshape(-1)
+
+
+def write_footage_bin(path, frames, bits, serials, timestamp=0, file_index=0, file_count=1):
+    """Writes a footage container (camera_isp/BinaryFootageFile.h:18-27, .cpp:178-201): a 32-byte header in a 4096-byte block, then
+    frames[f][c] (sample values (h, w): < 256 for 8 bits, < 4096 for 12) packed, frame f of camera c at 4096 + (n_cams * f + c) *
+    frame_bytes. Bytes 4..7 of every frame carry the camera's serial number, as the capture software stamps them (Unpacker.cpp:125).
+    Returns the packed frames [f][c] as written."""
+    n_cams = len(frames[0])
+    h, w = np.asarray(frames[0][0]).shape
+    hd = np.array([0xfaceb00c, timestamp, file_index, file_count, w, h, bits, n_cams], np.uint32)
+    packed_all = []
+    with open(path, "wb") as f:
+        f.write(hd.tobytes())
+        f.write(b"\0" * (4096 - 32))
+        for fr in frames:
+            row = []
+            for c, img in enumerate(fr):
+                p = pack12(img) if bits == 12 else np.asarray(img).astype(np.uint8).reshape(-1).copy()
+                p[4:8] = np.frombuffer(np.uint32(serials[c]).tobytes(), np.uint8)
+                f.write(p.tobytes())
+                row.append(p)
+            packed_all.append(row)
+    return packed_all

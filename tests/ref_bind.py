@@ -278,3 +278,59 @@ def isp_process_b200(json_text, raw, demosaic_filter=2, resize=1, output_bpp=8, 
                                   int(tone_curve), black_level_offset, int(swizzle), P(out)):
         raise RuntimeError(_IBLIB.refisp_last_error().decode())
     return out
+
+
+# ---- the reference's footage container reader and raw-sample converter (oracle/_ref/libref_unpack.so, oracle/ref_unpack_capi.cpp) ----
+REF_UNPACK_SO = os.path.join(ORACLE_DIR, "_ref", "libref_unpack.so")
+_ULIB = None
+
+
+def unpack_available():
+    return os.path.exists(REF_UNPACK_SO)
+
+
+def _unpack_lib():
+    global _ULIB
+    if _ULIB is None:
+        if not os.path.exists(REF_UNPACK_SO):
+            raise RuntimeError("oracle/_ref/libref_unpack.so is missing (oracle/ref_build.sh)")
+        _ULIB = C.CDLL(REF_UNPACK_SO)
+        _ULIB.refunpack_last_error.restype = C.c_char_p
+        _ULIB.refunpack_open.restype = C.c_void_p
+    return _ULIB
+
+
+def raw_convert(packed, bits, w, h):
+    """RawConverter::convert8Frame / convert12Frame (RawConverter.cpp:14-59): packed bytes -> (h, w) uint16."""
+    L = _unpack_lib()
+    packed = np.ascontiguousarray(packed, np.uint8)
+    out = np.zeros((h, w), np.uint16)
+    if L.refunpack_convert(P(packed), bits, w, h, P(out)):
+        raise RuntimeError(L.refunpack_last_error().decode())
+    return out
+
+
+class FootageFile:
+    """BinaryFootageFile of the reference build."""
+
+    def __init__(self, path):
+        L = _unpack_lib()
+        meta = (C.c_uint32 * 8)()
+        frames, fsize = C.c_uint64(), C.c_uint64()
+        self.h = L.refunpack_open(str(path).encode(), meta, C.byref(frames), C.byref(fsize))
+        if not self.h:
+            raise RuntimeError(L.refunpack_last_error().decode())
+        self.meta = list(meta)
+        self.frames, self.frame_size = frames.value, fsize.value
+
+    def frame(self, f, c):
+        L = _unpack_lib()
+        out = np.zeros(self.frame_size, np.uint8)
+        if L.refunpack_frame(C.c_void_p(self.h), f, c, P(out)):
+            raise RuntimeError(L.refunpack_last_error().decode())
+        return out
+
+    def close(self):
+        if self.h:
+            _unpack_lib().refunpack_close(C.c_void_p(self.h))
+            self.h = None

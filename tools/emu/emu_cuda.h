@@ -35,6 +35,7 @@ struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
+struct uint4 { unsigned x, y, z, w; };
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}

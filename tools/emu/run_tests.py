@@ -27,7 +27,7 @@ def build():
         if not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(os.path.join(CSRC, name + ".cu")), os.path.getmtime(os.path.join(HERE, "emu_cuda.h"))):
             subprocess.check_call(common + ["-o", obj, gen])
         objs.append(obj)
-    for src, obj in ((os.path.join(CSRC, "rig.cpp"), "rig_emu.o"), (os.path.join(HERE, "emu_rt.cpp"), "emu_rt.o")):
+    for src, obj in ((os.path.join(CSRC, "rig.cpp"), "rig_emu.o"), (os.path.join(CSRC, "footage.cpp"), "footage_emu.o"), (os.path.join(HERE, "emu_rt.cpp"), "emu_rt.o")):
         o = os.path.join(BUILD, obj)
         subprocess.check_call(common + ["-o", o, src])
         objs.append(o)
