@@ -17,7 +17,9 @@ ASM_RULES = [
     (r'asm volatile\("ld\.volatile\.global\.v2\.f32 \{%0,%1\}, \[%2\];" : "=f"\(v\.x\), "=f"\(v\.y\) : "l"\(p\) : "memory"\);', 'v = emu::ld_volatile(p);'),
     (r'asm volatile\("st\.volatile\.global\.v2\.f32 \[%0\], \{%1,%2\};" ::"l"\(p\), "f"\(v\.x\), "f"\(v\.y\) : "memory"\);', 'emu::st_volatile(p, v);'),
     (r'asm volatile\("ld\.global\.nc\.v8\.f32 \{%0,%1,%2,%3,%4,%5,%6,%7\}, \[%8\];"\s*:[^;]*?: "l"\(p\)\);', 'c.top = p[0]; c.bot = p[1];'),
-    (r'asm volatile\("prefetch\.global\.L1 \[%0\];" ::"l"\(nextLine\)\);', '(void)nextLine;'),
+    (r'asm volatile\("prefetch\.global\.L1 \[%0\];" ::"l"\(([^;]*)\)\);', r'(void)(\1);'),
+    # cp.async helpers: the emulator build takes their S360_EMU branch (synchronous copies); the PTX branch is never compiled
+    (r'asm volatile\("cp\.async\.[^;]*?;"[^;]*?\);', ';'),
     (r'asm\("min\.f32 %0, %1, %2, %3;" : "=f"\(r\) : "f"\(a\), "f"\(b\), "f"\(c\)\);[^\n]*', 'r = fminf(fminf(a, b), c);'),
     (r'asm\("max\.f32 %0, %1, %2, %3;" : "=f"\(r\) : "f"\(a\), "f"\(b\), "f"\(c\)\);', 'r = fmaxf(fmaxf(a, b), c);'),
 ]
@@ -113,7 +115,7 @@ def main(inp, outp):
             sys.exit('emu_prep: inline PTX without a rule:\n' + '\n'.join(left))
     modes = kernel_modes(src)
     src = rewrite_launches(src, modes)
-    open(outp, 'w').write('// generated by tools/emu/emu_prep.py from ' + inp + '\n' + src)
+    open(outp, 'w').write('// generated by tools/emu/emu_prep.py from ' + inp + '\n#define S360_EMU 1\n' + src)
     print({k: v.split('::')[1] for k, v in modes.items()})
 
 
