@@ -780,11 +780,10 @@ void checkFlowErrors(s360_ctx* c) {   // call after the context's stream has bee
   if (c->plan->prFlowBatch) c->plan->prFlowBatch->checkSweepError();
 }
 void collectProfile(s360_ctx* c) {
-  if (!c->plan) return;
   S360_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  if (c->plan->sideFlow) c->plan->sideFlow->collectProfile(&c->sweepProfile);
-  if (c->plan->poleFlowBatch) c->plan->poleFlowBatch->collectProfile(&c->sweepProfile);
-  c->kernelProf.collect();
+  if (c->plan && c->plan->sideFlow) c->plan->sideFlow->collectProfile(&c->sweepProfile);
+  if (c->plan && c->plan->poleFlowBatch) c->plan->poleFlowBatch->collectProfile(&c->sweepProfile);
+  c->kernelProf.collect();   // also without a frame plan: the ISP and the stand-alone operators profile through the same scopes
 }
 }
 s360_ctx::s360_ctx() {}
