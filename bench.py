@@ -405,6 +405,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--temporal", action="store_true", help="video mode: every context is a chain (frame i regularises against frame i-1 of its context)")
     ap.add_argument("--no-extras", action="store_true", help="skip the short 6k / cubemap passes appended to the headline line")
+    ap.add_argument("--latency-mode", action="store_true", help="run every context in latency mode (s360_ctx_set_latency_mode); the default is the throughput mode")
     ap.add_argument("--isp-only", action="store_true", help="only the soft-ISP pass of the extras (SURVEY 8 f2): prints its JSON object")
     ap.add_argument("--cpu-arm-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--worker-kind", default="reference", help=argparse.SUPPRESS)
@@ -481,6 +482,9 @@ def main():
     if args.temporal:
         for c in ctxs[1:]:
             c.set_temporal(True)
+    if args.latency_mode:
+        for c in ctxs:
+            c.set_latency_mode(True)
     img_h, img_w = frame_sets[0][0].shape[:2]
     n_cam = len(frame_sets[0])
     h2d_bytes = n_cam * img_w * img_h * 3
@@ -565,6 +569,28 @@ def main():
     ctxs[0].renderStereoPanorama(params, [t.numpy() for t in pinned_in[0]], pinned_out[0].numpy(), pinned_cube[0].numpy() if cw else None)
     stage_ms = ctxs[0].stage_ms()
     ctxs[0].set_graphs(True)
+    # the same frame alone in the other sweep mode (s360_ctx_set_latency_mode: cp.async input / footprint rings -- shorter alone, slower
+    # with many frames in flight, bit-identical): plan rebuilt, one warm frame, one stage-timed frame, CRC against the default mode's frame
+    import zlib
+    crc_mode_a = zlib.crc32(pinned_out[0].numpy().tobytes())
+    other = not args.latency_mode
+    ctxs[0].set_latency_mode(other)
+    ctxs[0].renderStereoPanorama(params, [t.numpy() for t in pinned_in[0]], pinned_out[0].numpy(), pinned_cube[0].numpy() if cw else None)
+    ctxs[0].set_graphs(False)
+    ctxs[0].renderStereoPanorama(params, [t.numpy() for t in pinned_in[0]], pinned_out[0].numpy(), pinned_cube[0].numpy() if cw else None)
+    stage_ms_other = ctxs[0].stage_ms()
+    ctxs[0].set_graphs(True)
+    if zlib.crc32(pinned_out[0].numpy().tobytes()) != crc_mode_a:
+        raise SystemExit("bench: latency mode and throughput mode rendered different frames")
+    ctxs[0].set_latency_mode(args.latency_mode)
+    for _ in range(2):   # rebuild the plan and re-capture the frame graph of the mode the rest of the run uses
+        ctxs[0].render_frame_dev(params, [t.data_ptr() for t in dev_in[0]], img_w, img_h, dev_out[0].data_ptr(), dev_cube[0].data_ptr() if cw else None)
+    ctxs[0].synchronize()
+    single_frame = {"sweep_mode_of_this_run": "latency" if args.latency_mode else "throughput",
+                    "throughput_mode_ms": (stage_ms_other if args.latency_mode else stage_ms)["total"],
+                    "latency_mode_ms": (stage_ms if args.latency_mode else stage_ms_other)["total"],
+                    "latency_mode_stages": stage_ms if args.latency_mode else stage_ms_other,
+                    "note": "one 8K frame alone on the GPU through the host API (stage timers); s360_ctx_set_latency_mode selects the sweep variant, results are bit-identical"}
 
     # every kernel of one frame rendered ALONE on the GPU with CUDA events around each launch (s360_profile_kernels): ms per frame,
     # algorithmic bytes per frame (compulsory reads + writes) and the fraction of the HBM roofline that gives
@@ -672,7 +698,7 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "roofline_all": roofline_all, "cpu_baseline": cpu_baseline,
         "output_crc32": {"graph_replay_frame0": f"{crc_graph:08x}", "host_api_frame0": f"{crc_host:08x}", "equal": True},
         "extra": extra,
-        "stage_ms_single_frame": stage_ms, "host_enqueue_ms_per_frame": 1000.0 * t_enq / (args.steps * F),
+        "stage_ms_single_frame": stage_ms, "single_frame_latency": single_frame, "host_enqueue_ms_per_frame": 1000.0 * t_enq / (args.steps * F),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

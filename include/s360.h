@@ -97,6 +97,11 @@ int s360_profile_enable(s360_ctx* ctx, int on);
 /* Whole-frame CUDA-graph replay (default on). Profiling, keep_intermediates and the stage timers
  * need the plain launch path and switch it off implicitly for the frames they cover. */
 int s360_ctx_set_graphs(s360_ctx* ctx, int on);
+/* Latency mode (default off): the optical-flow sweeps of this context run the kernel variant that shortens ONE frame (its inputs and the
+ * own-flow footprint of each pixel are staged through shared memory ahead of the dependent chain: about -7 % per 8K frame rendered alone)
+ * at the price of instructions and shared memory that lower the frame rate when many contexts render at once (about -2 % at 23 frames in
+ * flight). Use it for previews / single-frame renders; leave it off for batch throughput. Results are bit-identical in both modes. */
+int s360_ctx_set_latency_mode(s360_ctx* ctx, int on);
 /* Video mode (--prev_frame_data_dir != NONE, scripts/batch_process_video.py:137,157-158): when on, every frame
  * rendered on this context regularises its flows against the previous frame rendered on it (PixFlow.h:101-118,
  * 147-153, 165-167); the previous flows / overlap images / extended fisheye images stay on the device instead of

@@ -347,6 +347,10 @@ class Context:
     def set_graphs(self, on=True):
         _check(lib().s360_ctx_set_graphs(self.h, int(on)))
 
+    def set_latency_mode(self, on=True):
+        """s360_ctx_set_latency_mode: the sweep variant that shortens one frame rendered alone (bit-identical results)."""
+        _check(lib().s360_ctx_set_latency_mode(self.h, int(on)))
+
     def profile_enable(self, on=True):
         _check(lib().s360_profile_enable(self.h, int(on)))
 

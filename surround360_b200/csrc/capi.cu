@@ -133,6 +133,15 @@ int s360_ctx_set_graphs(s360_ctx* c, int on) {
   c->useGraphs = on != 0;
   S360_API_END
 }
+int s360_ctx_set_latency_mode(s360_ctx* c, int on) {
+  S360_API_BEGIN
+  require(c != nullptr, "null context");
+  if (c->latencyMode != (on != 0)) {
+    c->latencyMode = on != 0;
+    resetPlan(c);   // the frame plan's flow batches and its captured graph hold the kernel choice
+  }
+  S360_API_END
+}
 int s360_profile_enable(s360_ctx* c, int on) {
   S360_API_BEGIN
   require(c != nullptr, "null context");
@@ -316,6 +325,7 @@ int s360_flow_compute_batch(s360_ctx* c, const char* alg, int n, const uint8_t* 
     ip.hint[k] = hints ? (int)hints[k] : 0;
   }
   FlowBatch fb(n, w, h, fp);
+  fb.setLatencyMode(c->latencyMode);
   fb.run(st, ip, pv, dF.as<float2>());
   for (int k = 0; k < n; ++k) S360_CUDA_CHECK(cudaMemcpyAsync(flowOut[k], dF.as<float2>() + k * px, px * 8, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -347,6 +357,7 @@ int s360_flow_compute(s360_ctx* c, const char* alg, const uint8_t* i0, const uin
     pv.enabled = true; pv.prevFlow[0] = dPF.as<float2>(); pv.prevI1[0] = dP1.as<uchar4>(); pv.prevPitch[0] = w;
   }
   FlowBatch fb(1, w, h, fp, pv.enabled);
+  fb.setLatencyMode(c->latencyMode);
   fb.run(st, ip, pv, dF.as<float2>());
   S360_CUDA_CHECK(cudaMemcpyAsync(flowOut, dF.p, px * 8, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -385,6 +396,7 @@ int s360_flow_compute_strided(s360_ctx* c, const char* alg, const uint8_t* i0, s
     pv.enabled = true; pv.prevFlow[0] = dPF.as<float2>(); pv.prevI1[0] = dP1.as<uchar4>(); pv.prevPitch[0] = w;
   }
   FlowBatch fb(1, w, h, fp, pv.enabled);
+  fb.setLatencyMode(c->latencyMode);
   fb.run(st, ip, pv, dF.as<float2>());
   S360_CUDA_CHECK(cudaMemcpy2DAsync(flowOut, flowOutStride ? flowOutStride : rowF, dF.p, rowF, rowF, h, cudaMemcpyDeviceToHost, st));
   S360_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -406,6 +418,7 @@ int s360_flow_compute_dev(s360_ctx* c, const char* alg, const uint8_t* i0Dev, si
   const std::string key = std::string(alg) + ":" + std::to_string(w) + "x" + std::to_string(h);
   auto& slot = c->flowOps[key];
   if (!slot) slot = std::make_unique<FlowBatch>(1, w, h, fp);
+  slot->setLatencyMode(c->latencyMode);
   FlowImagePtrs ip{};
   FlowPrevPtrs pv{};
   ip.i0[0] = reinterpret_cast<const uchar4*>(i0Dev); ip.i1[0] = reinterpret_cast<const uchar4*>(i1Dev);

@@ -58,6 +58,7 @@ int run(int argc, char** argv) {
   if (L.w != R.w || L.h != R.h) throw VrCamException("left and right image differ in size");
   s360_ctx* ctx = nullptr;
   check(s360_ctx_create(std::atoi(v["device"].c_str()), &ctx));
+  check(s360_ctx_set_latency_mode(ctx, 1));   // one pair at a time: the latency variant of the sweeps (same bytes)
   std::vector<float> fLR((size_t)L.w * L.h * 2), fRL(fLR.size());
   const int reps = std::max(1, std::atoi(v["repetitions"].c_str()));
   for (int rep = 0; rep < reps; ++rep) {

@@ -33,10 +33,10 @@ struct Flags {
       {"eqr_width", "256"}, {"eqr_height", "128"}, {"final_eqr_width", "3480"}, {"final_eqr_height", "960"},
       {"cubemap_width", "1536"}, {"cubemap_height", "1536"}, {"cubemap_format", "video"},
       // additions of this build
-      {"save_flow_data", "true"}, {"device", "0"},
+      {"save_flow_data", "true"}, {"device", "0"}, {"latency_mode", "true"},
       // glog flags the driver script passes (scripts/batch_process_video.py:31-34): accepted
       {"logbuflevel", "0"}, {"log_dir", ""}, {"stderrthreshold", "2"}, {"v", "0"}, {"logtostderr", "false"}, {"alsologtostderr", "false"}};
-  const std::vector<std::string> bools = {"save_debug_images", "enable_top", "enable_bottom", "enable_pole_removal", "save_flow_data", "logtostderr", "alsologtostderr"};
+  const std::vector<std::string> bools = {"save_debug_images", "enable_top", "enable_bottom", "enable_pole_removal", "save_flow_data", "latency_mode", "logtostderr", "alsologtostderr"};
   bool isBool(const std::string& n) const { for (auto& b : bools) if (b == n) return true; return false; }
   void parse(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
@@ -125,6 +125,7 @@ int run(int argc, char** argv) {
   const double startTime = nowSec();
   s360_ctx* ctx = nullptr;
   check(s360_ctx_create(F.i("device"), &ctx));
+  check(s360_ctx_set_latency_mode(ctx, F.b("latency_mode") ? 1 : 0));   // one frame per process: the latency variant of the sweeps (same bytes)
   check(s360_rig_load_file(ctx, F.s("rig_json_file").c_str()));
   s360_params P;
   s360_params_default(&P);

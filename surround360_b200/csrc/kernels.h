@@ -190,6 +190,9 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   // sweep-kernel profiling: CUDA events around every k_sweep launch (on the launching stream)
   struct SweepProfile { double ms = 0, levelPixels = 0, steps = 0; unsigned long long launches = 0, fallbacks = 0; };
   void enableProfile(bool on) { profile_ = on; }
+  // latency mode: the sweeps run the cp.async-ring kernel (k_sweep<.., 4>), which shortens a frame rendered alone and costs throughput
+  // when many frames are in flight (flow_kernels.cu); results are bit-identical
+  void setLatencyMode(bool on);
   // call after the stream has been synchronised; accumulates and clears pending events
   void collectProfile(SweepProfile* acc);
   // after the stream has been synchronised: throws if a sweep band gave up waiting for its producer (see k_sweep's bounded spin)
@@ -202,6 +205,7 @@ class FlowBatch {  // PixFlow::computeOpticalFlow for n same-sized pairs, solved
   size_t totalBytes_ = 0;
   bool dump_ = false;
   bool profile_ = false;
+  bool latency_ = false;
   bool temporal_ = false, dumpAlloc_ = false;
   struct ProfRec { cudaEvent_t a, b; double px, steps; };
   std::vector<ProfRec> pending_;

@@ -271,6 +271,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
   S360_CUDA_CHECK(cudaMemsetAsync(F.panoR.p, 0, eqPx * 4, st));
   F.temporal = c->temporal;
   F.sideFlow = std::make_unique<FlowBatch>(2 * F.numCams, g.overlapW, g.camH, sideFP, F.temporal, false, true);
+  F.sideFlow->setLatencyMode(c->latencyMode);
   if (F.temporal) { F.prevProj.alloc(F.proj.bytes); F.prevFlowSide.alloc(F.flowSide.bytes); }
   if (F.nPole) {
     if (g.poleH > P.eqr_height) throw std::runtime_error("pole image taller than the equirect");
@@ -281,6 +282,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
     F.poleFlow.alloc(extPx * 8 * F.nPole);
     F.poleWarped.alloc(polePx * 4 * F.nPole);
     F.poleFlowBatch = std::make_unique<FlowBatch>(F.nPole, g.extW, g.poleH, poleFP, F.temporal, false, true);
+    F.poleFlowBatch->setLatencyMode(c->latencyMode);
     if (F.temporal) { F.prevExtFish.alloc(F.extFish.bytes); F.prevPoleFlow.alloc(F.poleFlow.bytes); }
     (void)c->blurKernelFor(P.std_alpha_feather_size);  // allocate now: nothing may allocate while a frame is captured
     F.poleRemoval = F.bottom && P.enable_pole_removal != 0;
@@ -292,6 +294,7 @@ static void buildPlan(s360_ctx* c, const s360_params& P, int imgW, int imgH) {
       F.prA.alloc(ipx * 4); F.prB.alloc(ipx * 4); F.prC.alloc(ipx * 4); F.prFlow.alloc(ipx * 8);
       F.prScratch.alloc(featherScratchBytes(imgW, imgH));
       F.prFlowBatch = std::make_unique<FlowBatch>(1, imgW, imgH, prFP, false, false, true);
+      F.prFlowBatch->setLatencyMode(c->latencyMode);
     }
   }
   F.eyes.alloc(eqPx * 4 * 2);   // both eyes back to back so one launch sharpens them together
@@ -754,6 +757,7 @@ void poleToSide(s360_ctx* c, const s360_params& P, const uint8_t* sideHost, int 
                       dExtS.as<uchar4>(), extW, dScr.as<uint8_t>());
   launchExtendWrap(st, dFish.as<uchar4>(), fw, fh, dExtF.as<uchar4>(), extW);
   FlowBatch fb(1, extW, fh, fp);
+  fb.setLatencyMode(c->latencyMode);
   FlowImagePtrs ip{};
   FlowPrevPtrs pv{};
   ip.i0[0] = dExtS.as<uchar4>(); ip.i1[0] = dExtF.as<uchar4>(); ip.pitch0[0] = ip.pitch1[0] = extW; ip.hint[0] = S360_HINT_DOWN;

@@ -56,6 +56,7 @@ struct s360_ctx {
   bool profile = false;
   bool profileKernels = false;          // s360_profile_enable(ctx, 2): events around every kernel launch (s360_profile_kernels)
   bool useGraphs = true;
+  bool latencyMode = false;             // s360_ctx_set_latency_mode: the flow batches run the latency variant of the sweep
   bool temporal = false;
   s360::FlowBatch::SweepProfile sweepProfile;
   std::map<std::string, std::unique_ptr<s360::FlowBatch>> flowOps;   // s360_flow_compute_dev: one solver per (algorithm, size)

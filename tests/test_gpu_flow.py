@@ -97,3 +97,27 @@ def test_many_bands(ctx, pair):
     a = np.ascontiguousarray(np.concatenate([i0[:, :96], i0[::-1, :96]], 0)[:898])
     b = np.ascontiguousarray(np.concatenate([i1[:, :96], i1[::-1, :96]], 0)[:898])
     check(ctx.computeOpticalFlow("pixflow_low", a, b, hint=2), ob.pixflow(a, b, "pixflow_low", hint=2))
+
+
+def test_latency_mode_is_bit_identical(ctx, pair):
+    """s360_ctx_set_latency_mode: the sweep variant with the cp.async input / footprint rings (k_sweep<.., 4>) against the oracle -- row
+    and column bands, many bands, ragged widths, gated regions, the search preset; and against the default kernel on the same inputs."""
+    i0, i1 = pair
+    cases = [(i0, i1, "pixflow_low", 3), (i0[:201, :333].copy(), i1[:201, :333].copy(), "pixflow_search_20", 2),
+             (i0[:130, :65].copy(), i1[:130, :65].copy(), "pixflow_low", 0)]
+    tall0 = np.ascontiguousarray(np.concatenate([i0[:, :96], i0[::-1, :96]], 0)[:898])
+    tall1 = np.ascontiguousarray(np.concatenate([i1[:, :96], i1[::-1, :96]], 0)[:898])
+    cases.append((tall0, tall1, "pixflow_low", 2))
+    g0, g1 = [x.copy() for x in pair]
+    g0[:, 200:260, 3] = 0
+    g1[100:180, :, 3] = 128
+    cases.append((g0[:256, :384].copy(), g1[:256, :384].copy(), "pixflow_low", 3))
+    normal = [ctx.computeOpticalFlow(alg, a, b, hint=h) for a, b, alg, h in cases]
+    ctx.set_latency_mode(True)
+    try:
+        for (a, b, alg, h), want in zip(cases, normal):
+            got = ctx.computeOpticalFlow(alg, a, b, hint=h)
+            assert np.array_equal(got, want)
+            check(got, ob.pixflow(a, b, alg, hint=h))
+    finally:
+        ctx.set_latency_mode(False)

@@ -135,6 +135,13 @@ def test_full_8k_properties(frames17):
     ov_r = np.ascontiguousarray(pb[:, :g.overlap_w])
     single = c.computeOpticalFlow("pixflow_low", ov_l, ov_r, hint=api.DirectionHint.LEFT)
     assert np.array_equal(single, c.intermediate("flowLtoR", 3))
+    # latency mode (s360_ctx_set_latency_mode: the sweep variant with the cp.async rings) renders the same bytes: through the plain
+    # launch path (first frame of a new plan) and through the re-captured graph
+    c.set_latency_mode(True)
+    assert np.array_equal(c.renderStereoPanorama(p, frames17), eq1)
+    assert np.array_equal(c.renderStereoPanorama(p, frames17), eq1)
+    c.set_latency_mode(False)
+    assert np.array_equal(c.renderStereoPanorama(p, frames17), eq1)
     c.close()
 
 

@@ -18,6 +18,7 @@ extern "C" int emu_flow_batch(const char* alg, int n, const uint8_t* const* i0, 
     s360::FlowParams P;
     if (!s360::flowParamsByName(alg, &P)) return 2;
     s360::FlowBatch fb(n, w, h, P);
+    if (std::getenv("S360_EMU_LATENCY")) fb.setLatencyMode(true);   // the cp.async-ring variant of the sweep (copies are synchronous here)
     s360::FlowImagePtrs ip{};
     s360::FlowPrevPtrs pv{};
     for (int k = 0; k < n; ++k) {
