@@ -85,6 +85,8 @@ static inline void __nanosleep(unsigned) {}
 static inline float __shfl_up_sync(unsigned, float v, unsigned d) { return emu::shfl_up(v, d); }
 static inline float __shfl_down_sync(unsigned, float v, unsigned d) { return emu::shfl_down(v, d); }
 static inline int __shfl_sync(unsigned, int v, int lane) { return emu::shfl_idx(v, lane); }
+static inline float __shfl_sync(unsigned, float v, int lane) { return __int_as_float(emu::shfl_idx(__float_as_int(v), lane)); }
+static inline void __syncwarp() { (void)emu::shfl_idx(0, 0); }   // every live lane of the warp arrives before any continues
 
 // ---- runtime API subset (device memory is host memory) ----
 typedef void* cudaStream_t;
