@@ -86,7 +86,8 @@ static inline float __shfl_up_sync(unsigned, float v, unsigned d) { return emu::
 static inline float __shfl_down_sync(unsigned, float v, unsigned d) { return emu::shfl_down(v, d); }
 static inline int __shfl_sync(unsigned, int v, int lane) { return emu::shfl_idx(v, lane); }
 static inline float __shfl_sync(unsigned, float v, int lane) { return __int_as_float(emu::shfl_idx(__float_as_int(v), lane)); }
-static inline void __syncwarp() { (void)emu::shfl_idx(0, 0); }   // every live lane of the warp arrives before any continues
+static inline void __syncwarp() { (void)emu::shfl_idx(0, 0); }
+static inline int __any_sync(unsigned, int pred) { int acc = 0; for (int l = 0; l < 32; ++l) acc |= emu::shfl_idx(pred ? 1 : 0, l); return acc; }   // full, converged warps only   // every live lane of the warp arrives before any continues
 
 // ---- runtime API subset (device memory is host memory) ----
 typedef void* cudaStream_t;
