@@ -392,6 +392,34 @@ def isp_pass(api, torch, dev, local_rank, peak, cpu=True):
     return res
 
 
+def nv12_pass(api, torch, dev, local_rank, peak, eq_w, eq_h):
+    """the finished stereo equirect (BGR8 in HBM) -> the NV12 surface a hardware encoder registers, on the device
+    (s360_frame_to_nv12_dev); CUDA events on the context's stream; algorithmic bytes 3 in + 1.5 out per pixel."""
+    ctx = api.Context(local_rank)
+    g = torch.Generator(device="cpu"); g.manual_seed(11)
+    frame = torch.randint(0, 256, (eq_h, eq_w, 3), dtype=torch.uint8, generator=g).to(dev)
+    y = torch.empty((eq_h, eq_w), dtype=torch.uint8, device=dev)
+    uv = torch.empty((eq_h // 2, eq_w), dtype=torch.uint8, device=dev)
+    st = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    for _ in range(3):
+        ctx.frame_to_nv12_dev(frame.data_ptr(), eq_w, eq_h, y.data_ptr(), uv.data_ptr(), matrix=1)
+    ctx.synchronize()
+    K = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(K):
+        ctx.frame_to_nv12_dev(frame.data_ptr(), eq_w, eq_h, y.data_ptr(), uv.data_ptr(), matrix=1)
+    e1.record(st)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    gbs = eq_w * eq_h * 4.5 / 1e9 / (ms / 1e3)
+    crc = format(zlib.crc32(y.cpu().numpy().tobytes() + uv.cpu().numpy().tobytes()), "08x")
+    ctx.close()
+    return {"workload": f"{eq_w}x{eq_h} BGR8 stereo equirect -> NV12 (BT.709 limited range), resident in HBM; the frame is 201 MB, larger than the L2",
+            "ms_per_frame": ms, "achieved_gbs": gbs, "frac": gbs / peak, "nv12_crc32": crc,
+            "note": "the image has no encoder library: the hand-off ends at the surface NVENC would register (INTEGRATION.md)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -679,6 +707,7 @@ def main():
         extra["video_8k_chains"] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, "8k", False, min(F, 12), steps=2, temporal=True)
         extra["video_8k_single_chain"] = side_pass(api, torch, dev, local_rank, blob_host, frame_sets, "8k", False, 1, steps=4, temporal=True)
         extra["isp_raw_to_bgr"] = isp_pass(api, torch, dev, local_rank, peak, cpu=not args.no_cpu_baseline)
+        extra["encode_handoff_nv12"] = nv12_pass(api, torch, dev, local_rank, peak, eq_w, eq_h)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

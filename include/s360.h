@@ -314,6 +314,18 @@ int s360_render_frame(s360_ctx* ctx, const s360_params* p, const uint8_t* const*
 int s360_render_frame_dev(s360_ctx* ctx, const s360_params* p, const uint8_t* const* images_bgr_dev, int img_w,
                           int img_h, uint8_t* equirect_out_dev, uint8_t* cubemap_out_dev);
 
+/* ---- encode hand-off ----
+ * The reference writes the equirect as PNG and lets ffmpeg convert to yuv420p and encode on the CPU (scripts/run_all.py:74-88, 313-330).
+ * Here the finished BGR8 frame (s360_render_frame_dev's output, still in HBM) is converted on the device to NV12 -- a w x h luma plane
+ * and an interleaved (w / 2) x (h / 2) Cb Cr plane, sizes rounded up for odd w / h -- the input surface a hardware encoder registers
+ * from a device pointer. matrix: 0 = BT.601 (what swscale applies to untagged RGB), 1 = BT.709; limited range; 8-bit integer form
+ * ((66 R + 129 G + 25 B + 128) >> 8) + 16 etc.; chroma from the rounded 2 x 2 mean. Pitches in bytes, 0 = tightly packed. The image has
+ * no encoder library, so the hand-off ends at the NV12 surface (INTEGRATION.md shows the NVENC calls that take it). */
+int s360_frame_to_nv12_dev(s360_ctx* ctx, const uint8_t* bgr_dev, size_t bgr_stride, int w, int h, int matrix, uint8_t* y_dev, size_t y_pitch,
+                           uint8_t* uv_dev, size_t uv_pitch);
+/* Host buffers: y_out w x h, uv_out (2 * ceil(w / 2)) x ceil(h / 2). */
+int s360_frame_to_nv12(s360_ctx* ctx, const uint8_t* bgr, int w, int h, int matrix, uint8_t* y_out, uint8_t* uv_out);
+
 /* Intermediates of the last s360_render_frame* call on this context, copied to host for
  * stage-wise parity tests. name: "projection"(idx=side cam) "flowLtoR"/"flowRtoL"(idx=pair)
  * "panoL" "panoR" "topSpherical" "bottomSpherical" "bottomMerged" "poleFlow"(0..3) "poleWarped"(0..3)

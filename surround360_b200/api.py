@@ -271,6 +271,18 @@ class Context:
         return out
 
     # ---- whole frame ----
+    def frame_to_nv12(self, bgr, matrix=0):
+        """Encode hand-off: (h, w, 3) BGR8 -> (y (h, w), uv (ceil(h / 2), 2 * ceil(w / 2))) NV12 planes."""
+        b = _c(bgr, np.uint8)
+        h, w = b.shape[:2]
+        y = np.zeros((h, w), np.uint8); uv = np.zeros(((h + 1) // 2, 2 * ((w + 1) // 2)), np.uint8)
+        _check(lib().s360_frame_to_nv12(self.h, _p(b), w, h, matrix, _p(y), _p(uv)))
+        return y, uv
+
+    def frame_to_nv12_dev(self, bgr_ptr, w, h, y_ptr, uv_ptr, matrix=0, bgr_stride=0, y_pitch=0, uv_pitch=0):
+        _check(lib().s360_frame_to_nv12_dev(self.h, C.c_void_p(bgr_ptr), C.c_size_t(bgr_stride), w, h, matrix, C.c_void_p(y_ptr), C.c_size_t(y_pitch),
+                                            C.c_void_p(uv_ptr), C.c_size_t(uv_pitch)))
+
     def output_size(self, params):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().s360_frame_output_size(self.h, C.byref(params), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

@@ -759,6 +759,36 @@ int s360_resize_cubic(s360_ctx* c, const uint8_t* src, int w, int h, int channel
   S360_API_END
 }
 
+int s360_frame_to_nv12_dev(s360_ctx* c, const uint8_t* bgrDev, size_t bgrStride, int w, int h, int matrix, uint8_t* yDev, size_t yPitch, uint8_t* uvDev,
+                           size_t uvPitch) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(bgrDev && yDev && uvDev && w > 0 && h > 0, "bad arguments");
+  require(matrix == 0 || matrix == 1, "matrix: 0 (BT.601) or 1 (BT.709)");
+  if (!bgrStride) bgrStride = (size_t)w * 3;
+  if (!yPitch) yPitch = (size_t)w;
+  if (!uvPitch) uvPitch = (size_t)((w + 1) / 2) * 2;
+  require(bgrStride >= (size_t)w * 3 && yPitch >= (size_t)w && uvPitch >= (size_t)((w + 1) / 2) * 2, "row pitch smaller than a row");
+  ProfActivate prof(c);
+  launchBgrToNv12(c->stream, bgrDev, bgrStride, w, h, matrix, yDev, yPitch, uvDev, uvPitch);
+  S360_API_END
+}
+int s360_frame_to_nv12(s360_ctx* c, const uint8_t* bgr, int w, int h, int matrix, uint8_t* yOut, uint8_t* uvOut) {
+  S360_API_BEGIN
+  useDevice(c);
+  require(bgr && yOut && uvOut && w > 0 && h > 0, "bad arguments");
+  require(matrix == 0 || matrix == 1, "matrix: 0 (BT.601) or 1 (BT.709)");
+  const size_t px = (size_t)w * h, cw = (size_t)((w + 1) / 2) * 2, chh = (size_t)(h + 1) / 2;
+  cudaStream_t st = c->stream;
+  DeviceBuffer dIn(px * 3), dY(px), dUV(cw * chh);
+  S360_CUDA_CHECK(cudaMemcpyAsync(dIn.p, bgr, px * 3, cudaMemcpyHostToDevice, st));
+  launchBgrToNv12(st, dIn.as<uint8_t>(), (size_t)w * 3, w, h, matrix, dY.as<uint8_t>(), (size_t)w, dUV.as<uint8_t>(), cw);
+  S360_CUDA_CHECK(cudaMemcpyAsync(yOut, dY.p, px, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaMemcpyAsync(uvOut, dUV.p, cw * chh, cudaMemcpyDeviceToHost, st));
+  S360_CUDA_CHECK(cudaStreamSynchronize(st));
+  S360_API_END
+}
+
 int s360_pole_to_side(s360_ctx* c, const s360_params* p, const uint8_t* side, int sw, int sh, const uint8_t* fish, int fw, int fh,
                       uint8_t* warpedOut, float* flowOut) {
   S360_API_BEGIN

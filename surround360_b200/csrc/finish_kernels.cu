@@ -473,4 +473,49 @@ void launchSharpen(cudaStream_t st, uchar4* img, int w, int h, int eyes, float a
   g_launchCount += 5;
 }
 
+// ------------------------------------------------------------------------------------
+// Encode hand-off: the finished BGR8 frame -> NV12 (a full-resolution luma plane and an interleaved half-resolution
+// Cb / Cr plane), the input surface a hardware encoder registers from a device pointer -- so that the equirects never leave HBM between
+// the renderer and the encoder (the reference writes PNGs and lets ffmpeg convert to yuv420p on the CPU, scripts/run_all.py:74-88).
+// Arithmetic: the 8-bit integer form of the limited-range ("TV") matrix, BT.601 (what swscale applies to untagged RGB by default) or
+// BT.709; chroma = the matrix applied to the rounded mean of the 2 x 2 block (centre siting). A thread owns one 2 x 2 block: 12 bytes in,
+// 6 bytes out, nothing else -- HBM-bound streaming.
+// ------------------------------------------------------------------------------------
+struct YuvCoef { int yr, yg, yb, ur, ug, ub, vr, vg, vb; };
+__global__ void __launch_bounds__(256)
+k_bgr_to_nv12(const uint8_t* __restrict__ bgr, size_t bgrStride, int w, int h, YuvCoef K, uint8_t* __restrict__ yPlane, size_t yPitch,
+              uint8_t* __restrict__ uvPlane, size_t uvPitch) {
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;   // 2 x 2 block index
+  const int x = bx * 2, y = by * 2;
+  if (x >= w || y >= h) return;
+  const int x1 = min(x + 1, w - 1), y1 = min(y + 1, h - 1);   // odd sizes: the last column / row is its own neighbour
+  const uint8_t* r0 = bgr + (size_t)y * bgrStride;
+  const uint8_t* r1 = bgr + (size_t)y1 * bgrStride;
+  int B[4], G[4], R[4];
+  const uint8_t* px[4] = {r0 + 3 * x, r0 + 3 * x1, r1 + 3 * x, r1 + 3 * x1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { B[k] = px[k][0]; G[k] = px[k][1]; R[k] = px[k][2]; }
+  auto luma = [&](int k) { return (uint8_t)(((K.yr * R[k] + K.yg * G[k] + K.yb * B[k] + 128) >> 8) + 16); };
+  yPlane[(size_t)y * yPitch + x] = luma(0);
+  if (x + 1 < w) yPlane[(size_t)y * yPitch + x + 1] = luma(1);
+  if (y + 1 < h) {
+    yPlane[(size_t)(y + 1) * yPitch + x] = luma(2);
+    if (x + 1 < w) yPlane[(size_t)(y + 1) * yPitch + x + 1] = luma(3);
+  }
+  const int rm = (R[0] + R[1] + R[2] + R[3] + 2) >> 2, gm = (G[0] + G[1] + G[2] + G[3] + 2) >> 2, bm = (B[0] + B[1] + B[2] + B[3] + 2) >> 2;
+  uint8_t* uv = uvPlane + (size_t)by * uvPitch + 2 * bx;
+  uv[0] = (uint8_t)(((K.ur * rm + K.ug * gm + K.ub * bm + 128) >> 8) + 128);
+  uv[1] = (uint8_t)(((K.vr * rm + K.vg * gm + K.vb * bm + 128) >> 8) + 128);
+}
+void launchBgrToNv12(cudaStream_t st, const uint8_t* bgr, size_t bgrStride, int w, int h, int matrix, uint8_t* yPlane, size_t yPitch, uint8_t* uvPlane,
+                     size_t uvPitch) {
+  // round(256 * 219/255 * (Kr, Kg, Kb)) and round(256 * 224/255 * chroma rows), chroma rows summing to zero (neutral greys get Cb = Cr = 128): BT.601 (Kr .299, Kb .114), BT.709 (Kr .2126, Kb .0722)
+  const YuvCoef k601{66, 129, 25, -38, -74, 112, 112, -94, -18}, k709{47, 157, 16, -26, -86, 112, 112, -102, -10};
+  const dim3 b(32, 8), g(iDivUp(iDivUp(w, 2), 32), iDivUp(iDivUp(h, 2), 8));
+  S360_PROF(st, "k_bgr_to_nv12", (double)w * h * 4.5);
+  k_bgr_to_nv12<<<g, b, 0, st>>>(bgr, bgrStride, w, h, matrix == 1 ? k709 : k601, yPlane, yPitch, uvPlane, uvPitch);
+  ++g_launchCount;
+  S360_CUDA_CHECK(cudaGetLastError());
+}
+
 }  // namespace s360

@@ -74,6 +74,9 @@ void launchCubemap(cudaStream_t st, const uchar4* eye, int w, int h, int faceW, 
 
 void launchPackBGR(cudaStream_t st, const uchar4* src, int w, int h, int pitch, uint8_t* dst);
 void launchUnpackBGRA(cudaStream_t st, const uint8_t* src, int channels, int w, int h, uchar4* dst);  // alpha=255 if 3ch
+// encode hand-off: BGR8 (row stride in bytes) -> NV12 planes; matrix 0 = BT.601, 1 = BT.709, limited range
+void launchBgrToNv12(cudaStream_t st, const uint8_t* bgr, size_t bgrStride, int w, int h, int matrix, uint8_t* yPlane, size_t yPitch, uint8_t* uvPlane,
+                     size_t uvPitch);
 void launchPackBGRA(cudaStream_t st, const uchar4* src, int w, int h, int pitch, uint8_t* dst);
 
 // ---------------- finish_kernels.cu ----------------
