@@ -13,8 +13,13 @@ from conftest import ROOT
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_flow_kernels_source_matches_oracle_under_host_emulation(tmp_path):
+@pytest.mark.parametrize("mode", ["throughput", "latency"])
+def test_flow_kernels_source_matches_oracle_under_host_emulation(tmp_path, mode):
+    """throughput: k_sweep<DIR, TR, 0>; latency: k_sweep_q (four lanes per pixel, cp.async rings copied synchronously by the emulator)."""
     env = dict(os.environ, EMU_BUILD=str(tmp_path / "emu"))
+    env.pop("S360_EMU_LATENCY", None)
+    if mode == "latency":
+        env["S360_EMU_LATENCY"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu", "check_flow.py"), "--sizes", "150x211"],
                        capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
