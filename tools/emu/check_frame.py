@@ -40,7 +40,31 @@ def frames():
     return synth.render_rig_frames(RIG17)
 
 
+def latency_frame():
+    """--latency: one frame with every context in latency mode (k_sweep_q inside the whole pipeline: side flows in column bands, pole flows
+    with their gated regions in row bands) against the oracle and against the default kernels."""
+    f0 = frames()
+    P = api.default_params(**KW)
+    t = time.time()
+    a = ctx()
+    a.set_latency_mode(True)
+    eq = a.renderStereoPanorama(P, f0).copy()
+    flows = [a.intermediate("flowLtoR", 3).copy(), a.intermediate("poleFlow", 1).copy()]
+    print(f"latency-mode frame emulated in {time.time() - t:.0f} s")
+    ref = ob.Rig.load(RIG17).render_frame(f0, ob.make_params(**KW))
+    ok = np.array_equal(eq, ref.get("equirect"))
+    print("latency-mode frame vs oracle:", "bit-exact" if ok else "MISMATCH")
+    a.set_latency_mode(False)
+    eq_t = a.renderStereoPanorama(P, f0)
+    ok2 = np.array_equal(eq, eq_t) and np.array_equal(flows[0], a.intermediate("flowLtoR", 3)) and np.array_equal(flows[1], a.intermediate("poleFlow", 1))
+    print("latency mode vs throughput mode (frame, a side flow, a pole flow):", "bit-exact" if ok2 else "MISMATCH")
+    a.close()
+    sys.exit(0 if ok and ok2 else 1)
+
+
 def main():
+    if "--latency" in sys.argv:
+        latency_frame()
     f0 = frames()
     f1 = [np.ascontiguousarray(np.roll(im, 5, axis=1)) for im in f0]
     P = api.default_params(**KW)
