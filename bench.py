@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--preset", default="8k", choices=["3k", "4k", "6k", "8k"])
     ap.add_argument("--cubemap", action="store_true", help="config 5: also produce the 1536^2 cubemap strip")
-    ap.add_argument("--inflight", type=int, default=24, help="frames in flight per GPU (contexts/streams); reduced to what fits in HBM (23 at the 8k preset)")
+    ap.add_argument("--inflight", type=int, default=23, help="frames in flight per GPU (contexts/streams); 23 contexts of 6.6 GiB fit in 180 GB at the 8k preset; reduced further if fewer fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--temporal", action="store_true", help="video mode: every context is a chain (frame i regularises against frame i-1 of its context)")
