@@ -402,11 +402,20 @@ k_iir_columns(const uchar4* __restrict__ inAll, int w, int n, float alpha, float
   const float om = 1.0f - alpha;
   const uchar4 p0 = in[x];
   float v0 = (float)p0.x, v1 = (float)p0.y, v2 = (float)p0.z;
+  // Both passes are software-pipelined: the loads of the next batch are in flight while the dependent multiply-adds of the current one
+  // run (one thread per line leaves only a few hundred warps on the GPU, so nothing else hides the round trip).
+  auto loadIn = [&](int j0, uchar4* d) {
+#pragma unroll
+    for (int u = 0; u < kIirBatch; ++u)
+      if (j0 + u <= n) d[u] = in[(size_t)iirBoundary<WRAP>(j0 + u, n) * w + x];
+  };
+  uchar4 nx[kIirBatch];
+  loadIn(1, nx);
   for (int j0 = 1; j0 <= n; j0 += kIirBatch) {  // causal: j = 1..n reads row boundary(j), writes row boundary(j-1)
     uchar4 ip[kIirBatch];
 #pragma unroll
-    for (int u = 0; u < kIirBatch; ++u)
-      if (j0 + u <= n) ip[u] = in[(size_t)iirBoundary<WRAP>(j0 + u, n) * w + x];
+    for (int u = 0; u < kIirBatch; ++u) ip[u] = nx[u];
+    if (j0 + kIirBatch <= n) loadIn(j0 + kIirBatch, nx);
 #pragma unroll
     for (int u = 0; u < kIirBatch; ++u)
       if (j0 + u <= n) {
@@ -417,14 +426,21 @@ k_iir_columns(const uchar4* __restrict__ inAll, int w, int n, float alpha, float
         buf[o] = v0; buf[plane + o] = v1; buf[2 * plane + o] = v2;
       }
   }
-  for (int j0 = n - 2; j0 >= -1; j0 -= kIirBatch) {  // anticausal: j = n-2..-1 reads buffer row boundary(j), writes row j+1
-    float b0[kIirBatch], b1[kIirBatch], b2[kIirBatch];
+  auto loadBuf = [&](int j0, float* d0, float* d1, float* d2) {
 #pragma unroll
     for (int u = 0; u < kIirBatch; ++u)
       if (j0 - u >= -1) {
         const size_t o = (size_t)iirBoundary<WRAP>(j0 - u, n) * w + x;
-        b0[u] = buf[o]; b1[u] = buf[plane + o]; b2[u] = buf[2 * plane + o];
+        d0[u] = buf[o]; d1[u] = buf[plane + o]; d2[u] = buf[2 * plane + o];
       }
+  };
+  float n0[kIirBatch], n1[kIirBatch], n2[kIirBatch];
+  loadBuf(n - 2, n0, n1, n2);
+  for (int j0 = n - 2; j0 >= -1; j0 -= kIirBatch) {  // anticausal: j = n-2..-1 reads buffer row boundary(j), writes row j+1
+    float b0[kIirBatch], b1[kIirBatch], b2[kIirBatch];
+#pragma unroll
+    for (int u = 0; u < kIirBatch; ++u) { b0[u] = n0[u]; b1[u] = n1[u]; b2[u] = n2[u]; }
+    if (j0 - kIirBatch >= -1) loadBuf(j0 - kIirBatch, n0, n1, n2);
 #pragma unroll
     for (int u = 0; u < kIirBatch; ++u)
       if (j0 - u >= -1) {
