@@ -5,6 +5,7 @@
 #include "emu_cuda.h"
 
 #include <ucontext.h>
+#include <mutex>
 
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
@@ -153,6 +154,10 @@ void st_volatile(float2* p, float2 v) {
 }
 
 void launch(const char* name, dim3 grid, dim3 block, Mode mode, const std::function<void()>& body) {
+  // one launch at a time: the execution model keeps per-launch state in globals (gridDim, static __shared__ arrays), so host threads that
+  // drive several contexts at once (the batch driver's chains) take turns
+  static std::mutex oneLaunch;
+  std::lock_guard<std::mutex> lock(oneLaunch);
   const unsigned nt = block.x * block.y * block.z;
   if (grid.x == 0 || grid.y == 0 || grid.z == 0 || nt == 0 || nt > 1024) {
     std::fprintf(stderr, "emu: bad launch configuration for %s\n", name);
